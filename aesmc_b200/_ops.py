@@ -1,0 +1,273 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (include/aesmc_b200.h).
+
+Everything here enqueues kernels of libaesmc_b200.so on torch's current CUDA stream; torch is used
+for device memory, streams and autograd bookkeeping only.  Tensors that arrive on the CPU (or numpy
+arrays, where the reference API accepts them) are staged through the GPU and the result is returned
+on the caller's device: there is no host implementation of any of these operations.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+_RESAMPLING_MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST}
+_default_mode = "exact"
+
+
+def set_resampling_mode(mode):
+    """'exact' (default): reference-order arithmetic, ancestor indices bit-identical to the
+    reference's numpy path.  'fast': parallel scan / approximate exp; statistically equivalent."""
+    global _default_mode
+    if mode not in _RESAMPLING_MODES:
+        raise ValueError("resampling mode must be 'exact' or 'fast', got {!r}".format(mode))
+    _default_mode = mode
+
+
+def get_resampling_mode():
+    return _default_mode
+
+
+def mode_code(mode=None):
+    return _RESAMPLING_MODES[_default_mode if mode is None else mode]
+
+
+def device():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(t, dtype=None):
+    """Contiguous CUDA view/copy of a tensor (staging CPU inputs onto the GPU)."""
+    if not t.is_cuda:
+        t = t.to(device(), non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def new_flags(dev=None):
+    return torch.zeros(1, dtype=torch.int32, device=dev or device())
+
+
+def raise_on_flags(flags, where="log_weight"):
+    """One host read of the device flag word; maps to the reference's exceptions."""
+    bits = int(flags.item())
+    if bits & _lib.FLAG_NAN:
+        raise FloatingPointError("log_weight contains nan element(s)")  # inference.py:244-245
+    if bits & _lib.FLAG_DEGENERATE:
+        raise FloatingPointError(
+            "{}: a row has no finite positive normaliser (all -inf or +inf); the reference would "
+            "silently emit out-of-range ancestor indices here".format(where))
+    if bits & _lib.FLAG_INDEX_RANGE:
+        raise IndexError("ancestral_index out of range [0, num_particles)")
+
+
+# ------------------------------------------------------------------------------------------------
+# fused SMC step
+# ------------------------------------------------------------------------------------------------
+class _SMCStep(torch.autograd.Function):
+    """log_w = (a + b) - c ; lse = logsumexp_k log_w ; idx = systematic ancestors(log_w, u) ;
+    x_out = x[idx]   (inference.py:97-104,125-126,130,234-269; state.py:158-183)."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, x, u, flags, mode, resample):
+        B, K = a.shape
+        log_w = torch.empty_like(a)
+        lse = torch.empty(B, dtype=torch.float32, device=a.device)
+        idx = torch.empty((B, K), dtype=torch.int32, device=a.device) if resample else None
+        x_out = None
+        D = 1
+        if resample and x is not None:
+            D = x[0, 0].numel()
+            x_out = torch.empty_like(x)
+        _lib.call("aesmc_smc_step_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(u), B, K,
+                  _lib.ptr(log_w), _lib.ptr(lse), _lib.ptr(idx), _lib.ptr(x if x_out is not None else None),
+                  _lib.ptr(x_out), D, _lib.ptr(flags), mode)
+        ctx.save_for_backward(log_w, lse, idx)
+        ctx.has = (b is not None, c is not None, x_out is not None)
+        ctx.x_shape = None if x is None else x.shape
+        if idx is not None:
+            ctx.mark_non_differentiable(idx)
+        outs = (log_w, lse, idx if idx is not None else torch.empty(0, device=a.device),
+                x_out if x_out is not None else torch.empty(0, device=a.device))
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_log_w, g_lse, _g_idx, g_x):
+        log_w, lse, idx = ctx.saved_tensors
+        has_b, has_c, has_x = ctx.has
+        B, K = log_w.shape
+        g_pos = g_neg = None
+        if g_log_w is not None or g_lse is not None:
+            g_log_w = None if g_log_w is None else g_log_w.contiguous()
+            g_lse = None if g_lse is None else g_lse.contiguous()
+            g_pos = torch.empty_like(log_w)
+            g_neg = torch.empty_like(log_w) if has_c else None
+            _lib.call("aesmc_step_bwd_f32", _lib.ptr(log_w), _lib.ptr(lse), _lib.ptr(g_log_w),
+                      _lib.ptr(g_lse), B, K, _lib.ptr(g_pos), _lib.ptr(g_neg))
+        gx = None
+        if has_x and g_x is not None and ctx.needs_input_grad[3]:
+            g_x = g_x.contiguous()
+            gx = torch.empty_like(g_x)
+            D = g_x[0, 0].numel()
+            _lib.call("aesmc_gather_bwd_f32", _lib.ptr(g_x), _lib.ptr(idx), 0, B, K, D, _lib.ptr(gx), 1)
+        return g_pos, (g_pos if has_b else None), g_neg, gx, None, None, None, None
+
+
+def smc_step(a, b, c, u, x, flags, mode=None, resample=True):
+    """Run one fused step.  a [B,K] float32 CUDA; b, c same or None; u [B] float64 (needed iff
+    resample); x [B,K,...] float32 or None.  Returns (log_w, lse, idx_int32 | None, x_resampled | None)."""
+    log_w, lse, idx, x_out = _SMCStep.apply(a, b, c, x, u, flags, mode_code(mode), resample)
+    return log_w, lse, (idx if resample else None), (x_out if (resample and x is not None) else None)
+
+
+def resample_from_weights(w, u, flags, mode=None):
+    """Systematic ancestors from normalised weights [B,K] (cumulative sum onwards); int32 [B,K]."""
+    B, K = w.shape
+    idx = torch.empty((B, K), dtype=torch.int32, device=w.device)
+    _lib.call("aesmc_resample_from_weights_f32", _lib.ptr(w), _lib.ptr(u), B, K, _lib.ptr(idx), _lib.ptr(flags),
+              mode_code(mode))
+    return idx
+
+
+def resample_from_cdf(cdf, u, flags):
+    """Systematic ancestors from a normalised CDF [B,K] (search only); int32 [B,K]."""
+    B, K = cdf.shape
+    idx = torch.empty((B, K), dtype=torch.int32, device=cdf.device)
+    _lib.call("aesmc_resample_from_cdf_f32", _lib.ptr(cdf), _lib.ptr(u), B, K, _lib.ptr(idx), _lib.ptr(flags))
+    return idx
+
+
+# ------------------------------------------------------------------------------------------------
+# ancestral gather
+# ------------------------------------------------------------------------------------------------
+class _Gather(torch.autograd.Function):
+    """state.resample for one tensor: out[b,k,...] = value[b, idx[b,k], ...] (state.py:158-183)."""
+
+    @staticmethod
+    def forward(ctx, value, idx, sorted_rows, flags):
+        B, K = value.shape[:2]
+        out = torch.empty_like(value)
+        row_bytes = value[0, 0].numel() * value.element_size()
+        _lib.call("aesmc_gather_bytes", _lib.ptr(value), _lib.ptr(idx), int(idx.dtype == torch.int64), B, K,
+                  row_bytes, _lib.ptr(out), _lib.ptr(flags))
+        ctx.save_for_backward(idx)
+        ctx.sorted_rows = sorted_rows
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, K = g.shape[:2]
+        D = g[0, 0].numel()
+        dt = g.dtype
+        if dt not in (torch.float32, torch.float64):
+            g = g.float()
+        g = g.contiguous()
+        gsrc = torch.empty_like(g)
+        fn = "aesmc_gather_bwd_f32" if g.dtype == torch.float32 else "aesmc_gather_bwd_f64"
+        _lib.call(fn, _lib.ptr(g), _lib.ptr(idx), int(idx.dtype == torch.int64), B, K, D, _lib.ptr(gsrc),
+                  int(ctx.sorted_rows))
+        return gsrc.to(dt), None, None, None
+
+
+def gather(value, idx, sorted_rows=False, flags=None):
+    """value [B,K,...] CUDA contiguous, idx [B,K] int32/int64 CUDA contiguous."""
+    if value.numel() == 0:
+        return value.clone()
+    return _Gather.apply(value, idx, sorted_rows, flags)
+
+
+# ------------------------------------------------------------------------------------------------
+# reductions / elementwise companions
+# ------------------------------------------------------------------------------------------------
+class _LogSumExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lw, flags):
+        B, K = lw.shape
+        out = torch.empty(B, dtype=lw.dtype, device=lw.device)
+        fn = "aesmc_logsumexp_f32" if lw.dtype == torch.float32 else "aesmc_logsumexp_f64"
+        _lib.call(fn, _lib.ptr(lw), B, K, _lib.ptr(out), _lib.ptr(flags))
+        ctx.save_for_backward(lw, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lw, lse = ctx.saved_tensors
+        if lw.dtype != torch.float32:
+            return g.unsqueeze(1) * torch.exp(lw - lse.unsqueeze(1)), None
+        B, K = lw.shape
+        out = torch.empty_like(lw)
+        _lib.call("aesmc_step_bwd_f32", _lib.ptr(lw), _lib.ptr(lse), None, _lib.ptr(g.contiguous()), B, K,
+                  _lib.ptr(out), None)
+        return out, None
+
+
+def logsumexp_rows(lw, flags=None):
+    """[B,K] float32/float64 CUDA contiguous -> [B]; differentiable."""
+    return _LogSumExp.apply(lw, flags)
+
+
+def is_accumulate(a, b, c, acc, first):
+    _lib.call("aesmc_is_accumulate_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(acc), None, a.numel(),
+              int(first))
+
+
+def lognormexp_rows(lw, exponentiate):
+    B, K = lw.shape
+    out = torch.empty_like(lw)
+    _lib.call("aesmc_lognormexp_f32", _lib.ptr(lw), B, K, _lib.ptr(out), int(exponentiate))
+    return out
+
+
+def log_ess_rows(lw):
+    B, K = lw.shape
+    out = torch.empty(B, dtype=lw.dtype, device=lw.device)
+    fn = "aesmc_log_ess_f32" if lw.dtype == torch.float32 else "aesmc_log_ess_f64"
+    _lib.call(fn, _lib.ptr(lw), B, K, _lib.ptr(out))
+    return out
+
+
+def weighted_moments(x, lw, want_second=True):
+    """x [B,K,D] float32, lw [B,K] float32 -> (mean [B,D], second [B,D] | None)."""
+    B, K = lw.shape
+    D = x[0, 0].numel()
+    mean = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    second = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_second else None
+    _lib.call("aesmc_weighted_moments_f32", _lib.ptr(x), _lib.ptr(lw), B, K, D, _lib.ptr(mean), _lib.ptr(second))
+    return mean, second
+
+
+def compose_index(prev, cur):
+    B, K = prev.shape
+    out = torch.empty_like(prev)
+    _lib.call("aesmc_compose_index_i32", _lib.ptr(prev), _lib.ptr(cur), B, K, _lib.ptr(out))
+    return out
+
+
+def iota_index(B, K, dev):
+    out = torch.empty((B, K), dtype=torch.int32, device=dev)
+    _lib.call("aesmc_iota_index_i32", B, K, _lib.ptr(out))
+    return out
+
+
+def widen_index(idx32):
+    out = torch.empty(idx32.shape, dtype=torch.int64, device=idx32.device)
+    _lib.call("aesmc_index_widen", _lib.ptr(idx32), _lib.ptr(out), idx32.numel())
+    return out
+
+
+def narrow_index(idx64):
+    out = torch.empty(idx64.shape, dtype=torch.int32, device=idx64.device)
+    _lib.call("aesmc_index_narrow", _lib.ptr(idx64), _lib.ptr(out), idx64.numel())
+    return out
+
+
+def uniforms_to_device(u, B, dev):
+    """Per-row float64 uniforms as a contiguous CUDA tensor [B]."""
+    if isinstance(u, np.ndarray):
+        u = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64))
+    u = u.reshape(B)
+    if u.dtype != torch.float64:
+        u = u.double()
+    return u.to(dev, non_blocking=True).contiguous()

@@ -1,0 +1,234 @@
+// api.cu -- the extern "C" surface declared in include/aesmc_b200.h: argument validation, error
+// strings, launch accounting.  No torch types, no allocation, no synchronisation.
+#include "common.cuh"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+namespace aesmc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return AESMC_ERR_LAUNCH;
+    }
+    return AESMC_OK;
+}
+
+// kernels (smc_step.cu, reduce.cu, gather.cu)
+int64_t max_particles_single_cta();
+int launch_smc_step(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
+                    int32_t *, const float *, float *, int64_t, int32_t *, int, int, cudaStream_t);
+int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
+int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
+int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
+int launch_log_ess_f32(const float *, int64_t, int64_t, float *, cudaStream_t);
+int launch_log_ess_f64(const double *, int64_t, int64_t, double *, cudaStream_t);
+int launch_step_bwd_f32(const float *, const float *, const float *, const float *, int64_t, int64_t, float *,
+                        float *, cudaStream_t);
+int launch_is_accumulate_f32(const float *, const float *, const float *, float *, float *, int64_t, int, cudaStream_t);
+int launch_weighted_moments_f32(const float *, const float *, int64_t, int64_t, int64_t, float *, float *, cudaStream_t);
+int launch_gather_bytes(const void *, const void *, int, int64_t, int64_t, int64_t, void *, int32_t *, cudaStream_t);
+int launch_gather_bwd_f32(const float *, const void *, int, int64_t, int64_t, int64_t, float *, int, cudaStream_t);
+int launch_gather_bwd_f64(const double *, const void *, int, int64_t, int64_t, int64_t, double *, int, cudaStream_t);
+int launch_compose_index(const int32_t *, const int32_t *, int64_t, int64_t, int32_t *, cudaStream_t);
+int launch_iota_index(int64_t, int64_t, int32_t *, cudaStream_t);
+int launch_index_widen(const int32_t *, int64_t *, int64_t, cudaStream_t);
+int launch_index_narrow(const int64_t *, int32_t *, int64_t, cudaStream_t);
+
+} // namespace aesmc
+
+using namespace aesmc;
+
+#define REQUIRE(cond, fn)                                                            \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            set_error("%s: invalid argument: %s", fn, #cond);                        \
+            return AESMC_ERR_BAD_ARG;                                                \
+        }                                                                            \
+    } while (0)
+
+static inline cudaStream_t S(void *s) { return static_cast<cudaStream_t>(s); }
+static const int64_t kMaxDim = 2147483647LL;
+
+extern "C" {
+
+int aesmc_version(void) { return 100; }
+const char *aesmc_last_error_string(void) { return g_err; }
+int64_t aesmc_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t aesmc_max_particles_single_cta(void) { return max_particles_single_cta(); }
+
+int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u, int64_t B,
+                       int64_t K, float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out,
+                       int64_t D, int32_t *flags, int mode, void *stream)
+{
+    const char *fn = "aesmc_smc_step_f32";
+    REQUIRE(lp_a && log_w && flags, fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
+    REQUIRE((idx == nullptr) || (u != nullptr), fn);
+    REQUIRE((x_in == nullptr) == (x_out == nullptr), fn);
+    REQUIRE(x_in == nullptr || (idx != nullptr && D >= 1 && K * D <= kMaxDim), fn);
+    REQUIRE(log_w != lp_a && log_w != lp_b && log_w != lp_c, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_smc_step(lp_a, lp_b, lp_c, u, B, K, log_w, lse, idx, x_in, x_out, x_in ? D : 1, flags, mode, 0, S(stream));
+}
+
+int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,
+                                    int32_t *flags, int mode, void *stream)
+{
+    const char *fn = "aesmc_resample_from_weights_f32";
+    REQUIRE(w && u && idx && flags, fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_smc_step(w, nullptr, nullptr, u, B, K, nullptr, nullptr, idx, nullptr, nullptr, 1, flags, mode, 1, S(stream));
+}
+
+int aesmc_resample_from_cdf_f32(const float *cdf, const double *u, int64_t B, int64_t K, int32_t *idx,
+                                int32_t *flags, void *stream)
+{
+    const char *fn = "aesmc_resample_from_cdf_f32";
+    REQUIRE(cdf && u && idx && flags, fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_smc_step(cdf, nullptr, nullptr, u, B, K, nullptr, nullptr, idx, nullptr, nullptr, 1, flags,
+                           AESMC_MODE_EXACT, 2, S(stream));
+}
+
+int aesmc_is_accumulate_f32(const float *lp_a, const float *lp_b, const float *lp_c, float *acc, float *log_w,
+                            int64_t n, int first, void *stream)
+{
+    const char *fn = "aesmc_is_accumulate_f32";
+    REQUIRE(lp_a && acc && n >= 0, fn);
+    if (n == 0) return AESMC_OK;
+    return launch_is_accumulate_f32(lp_a, lp_b, lp_c, acc, log_w, n, first, S(stream));
+}
+
+int aesmc_logsumexp_f32(const float *log_w, int64_t B, int64_t K, float *lse, int32_t *flags, void *stream)
+{
+    const char *fn = "aesmc_logsumexp_f32";
+    REQUIRE(log_w && lse && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_logsumexp_f32(log_w, B, K, lse, flags, S(stream));
+}
+int aesmc_logsumexp_f64(const double *log_w, int64_t B, int64_t K, double *lse, int32_t *flags, void *stream)
+{
+    const char *fn = "aesmc_logsumexp_f64";
+    REQUIRE(log_w && lse && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_logsumexp_f64(log_w, B, K, lse, flags, S(stream));
+}
+
+int aesmc_step_bwd_f32(const float *log_w, const float *lse, const float *g_log_w, const float *g_lse, int64_t B,
+                       int64_t K, float *g_pos, float *g_neg, void *stream)
+{
+    const char *fn = "aesmc_step_bwd_f32";
+    REQUIRE(g_pos && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(g_lse == nullptr || (log_w && lse), fn);
+    if (B == 0) return AESMC_OK;
+    return launch_step_bwd_f32(log_w, lse, g_log_w, g_lse, B, K, g_pos, g_neg, S(stream));
+}
+
+int aesmc_lognormexp_f32(const float *log_w, int64_t B, int64_t K, float *out, int exponentiate, void *stream)
+{
+    const char *fn = "aesmc_lognormexp_f32";
+    REQUIRE(log_w && out && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_lognormexp_f32(log_w, B, K, out, exponentiate, S(stream));
+}
+
+int aesmc_gather_bytes(const void *src, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t row_bytes,
+                       void *dst, int32_t *flags, void *stream)
+{
+    const char *fn = "aesmc_gather_bytes";
+    REQUIRE(src && idx && dst && src != dst, fn);
+    REQUIRE(B >= 0 && K >= 1 && row_bytes >= 1 && B <= kMaxDim && K * row_bytes <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_gather_bytes(src, idx, idx_is_i64, B, K, row_bytes, dst, flags, S(stream));
+}
+
+int aesmc_gather_bwd_f32(const float *gdst, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t D,
+                         float *gsrc, int sorted, void *stream)
+{
+    const char *fn = "aesmc_gather_bwd_f32";
+    REQUIRE(gdst && idx && gsrc && B >= 0 && K >= 1 && D >= 1 && B <= kMaxDim && K * D <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_gather_bwd_f32(gdst, idx, idx_is_i64, B, K, D, gsrc, sorted, S(stream));
+}
+int aesmc_gather_bwd_f64(const double *gdst, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t D,
+                         double *gsrc, int sorted, void *stream)
+{
+    const char *fn = "aesmc_gather_bwd_f64";
+    REQUIRE(gdst && idx && gsrc && B >= 0 && K >= 1 && D >= 1 && B <= kMaxDim && K * D <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_gather_bwd_f64(gdst, idx, idx_is_i64, B, K, D, gsrc, sorted, S(stream));
+}
+
+int aesmc_compose_index_i32(const int32_t *prev, const int32_t *cur, int64_t B, int64_t K, int32_t *out, void *stream)
+{
+    const char *fn = "aesmc_compose_index_i32";
+    REQUIRE(prev && cur && out && out != prev && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_compose_index(prev, cur, B, K, out, S(stream));
+}
+int aesmc_iota_index_i32(int64_t B, int64_t K, int32_t *out, void *stream)
+{
+    const char *fn = "aesmc_iota_index_i32";
+    REQUIRE(out && B >= 0 && K >= 1 && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_iota_index(B, K, out, S(stream));
+}
+int aesmc_index_widen(const int32_t *in, int64_t *out, int64_t n, void *stream)
+{
+    const char *fn = "aesmc_index_widen";
+    REQUIRE(in && out && n >= 0, fn);
+    if (n == 0) return AESMC_OK;
+    return launch_index_widen(in, out, n, S(stream));
+}
+int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream)
+{
+    const char *fn = "aesmc_index_narrow";
+    REQUIRE(in && out && n >= 0, fn);
+    if (n == 0) return AESMC_OK;
+    return launch_index_narrow(in, out, n, S(stream));
+}
+
+int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream)
+{
+    const char *fn = "aesmc_log_ess_f32";
+    REQUIRE(log_w && out && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_log_ess_f32(log_w, B, K, out, S(stream));
+}
+int aesmc_log_ess_f64(const double *log_w, int64_t B, int64_t K, double *out, void *stream)
+{
+    const char *fn = "aesmc_log_ess_f64";
+    REQUIRE(log_w && out && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_log_ess_f64(log_w, B, K, out, S(stream));
+}
+
+int aesmc_weighted_moments_f32(const float *x, const float *log_w, int64_t B, int64_t K, int64_t D, float *mean,
+                               float *second, void *stream)
+{
+    const char *fn = "aesmc_weighted_moments_f32";
+    REQUIRE(x && log_w && mean && B >= 0 && K >= 1 && D >= 1 && B <= kMaxDim && K * D <= kMaxDim, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_weighted_moments_f32(x, log_w, B, K, D, mean, second, S(stream));
+}
+
+} // extern "C"

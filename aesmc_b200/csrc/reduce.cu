@@ -1,0 +1,291 @@
+// reduce.cu -- row reductions and elementwise companions of the SMC step (HBM-bound, no tensor cores):
+//   logsumexp over particles      inference.py:130,158 / statistics.py:90-91
+//   step backward                  autograd of torch.logsumexp + the (a + b) - c sum
+//   lognormexp / exponentiate_and_normalize   math.py:6-51 (torch branch)
+//   log_ess                        statistics.py:79-91
+//   weighted moments               statistics.py:7-76 with f = x, x^2
+//   importance-sampling accumulate inference.py:156-157
+#include "common.cuh"
+
+namespace aesmc {
+
+template <typename T> struct Acc;
+template <> struct Acc<float> {
+    using OpMax = OpMaxF; using OpSum = OpSumF;
+    __device__ static float ninf() { return -INFINITY; }
+    __device__ static float ex(float x) { return expf(x); }
+    __device__ static float lg(float x) { return logf(x); }
+    __device__ static float mx(float a, float b) { return fmaxf(a, b); }
+};
+template <> struct Acc<double> {
+    using OpMax = OpMaxD; using OpSum = OpSumD;
+    __device__ static double ninf() { return -INFINITY; }
+    __device__ static double ex(double x) { return exp(x); }
+    __device__ static double lg(double x) { return log(x); }
+    __device__ static double mx(double a, double b) { return fmax(a, b); }
+};
+
+// Row max and NaN flag; every thread of the CTA gets the result.
+template <typename T>
+__device__ __forceinline__ T row_max(const T *__restrict__ row, int K, T *scratch, int *has_nan)
+{
+    T m = Acc<T>::ninf();
+    int bad = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const T v = row[k];
+        bad |= (v != v);
+        m = Acc<T>::mx(m, v);
+    }
+    m = block_allreduce(m, Acc<T>::ninf(), typename Acc<T>::OpMax(), scratch);
+    *has_nan = __syncthreads_or(bad);
+    return m;
+}
+
+template <typename T>
+__global__ void logsumexp_rows_kernel(const T *__restrict__ lw, int B, int K, T *__restrict__ lse, int32_t *flags)
+{
+    __shared__ T scratch[32];
+    for (int row = blockIdx.x; row < B; row += gridDim.x) {
+        const T *r = lw + (size_t)row * K;
+        int bad;
+        const T m = row_max(r, K, scratch, &bad);
+        T out;
+        if (bad) {
+            out = m + (T)NAN;
+            if (threadIdx.x == 0 && flags) atomicOr(flags, AESMC_FLAG_NAN);
+        } else if (!(fabs((double)m) < INFINITY)) {
+            out = m; // all -inf -> -inf ; +inf present -> +inf (torch.logsumexp convention)
+        } else {
+            T s = 0;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) s += Acc<T>::ex(r[k] - m);
+            s = block_allreduce(s, (T)0, typename Acc<T>::OpSum(), scratch);
+            out = m + Acc<T>::lg(s);
+        }
+        if (threadIdx.x == 0) lse[row] = out;
+    }
+}
+
+// out = lw - lse (exponentiate=0) or exp(lw - lse)
+__global__ void lognormexp_kernel(const float *__restrict__ lw, int B, int K, float *__restrict__ out, int exponentiate)
+{
+    __shared__ float scratch[32];
+    for (int row = blockIdx.x; row < B; row += gridDim.x) {
+        const float *r = lw + (size_t)row * K;
+        float *o = out + (size_t)row * K;
+        int bad;
+        const float m = row_max(r, K, scratch, &bad);
+        float lse;
+        if (bad) lse = NAN;
+        else if (!(fabsf(m) < INFINITY)) lse = m;
+        else {
+            float s = 0.f;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) s += expf(r[k] - m);
+            s = block_allreduce(s, 0.f, OpSumF(), scratch);
+            lse = m + logf(s);
+        }
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float d = r[k] - lse;
+            o[k] = exponentiate ? expf(d) : d;
+        }
+    }
+}
+
+template <typename T>
+__global__ void log_ess_kernel(const T *__restrict__ lw, int B, int K, T *__restrict__ out)
+{
+    __shared__ T scratch[32];
+    for (int row = blockIdx.x; row < B; row += gridDim.x) {
+        const T *r = lw + (size_t)row * K;
+        int bad;
+        const T m = row_max(r, K, scratch, &bad);
+        T s1 = 0, s2 = 0;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const T e = Acc<T>::ex(r[k] - m);
+            s1 += e;
+            s2 += e * e;
+        }
+        s1 = block_allreduce(s1, (T)0, typename Acc<T>::OpSum(), scratch);
+        s2 = block_allreduce(s2, (T)0, typename Acc<T>::OpSum(), scratch);
+        // 2*(m + log s1) - (2m + log s2)
+        if (threadIdx.x == 0) out[row] = bad ? (T)NAN : (T)2 * Acc<T>::lg(s1) - Acc<T>::lg(s2);
+    }
+}
+
+// g = g_log_w + g_lse[b] * exp(log_w - lse[b]);  g_pos = g, g_neg = -g
+__global__ void step_bwd_kernel(const float *__restrict__ lw, const float *__restrict__ lse,
+                                const float *__restrict__ glw, const float *__restrict__ glse, int64_t n4,
+                                int K, float *__restrict__ gpos, float *__restrict__ gneg)
+{
+    // vector path: K % 4 == 0 so a float4 never straddles two rows
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t row = (i * 4) / K;
+        float4 g = glw ? __ldcs(reinterpret_cast<const float4 *>(glw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (glse) {
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(lw) + i);
+            const float l = __ldg(lse + row), s = __ldg(glse + row);
+            g.x = fmaf(s, expf(v.x - l), g.x);
+            g.y = fmaf(s, expf(v.y - l), g.y);
+            g.z = fmaf(s, expf(v.z - l), g.z);
+            g.w = fmaf(s, expf(v.w - l), g.w);
+        }
+        __stcs(reinterpret_cast<float4 *>(gpos) + i, g);
+        if (gneg) __stcs(reinterpret_cast<float4 *>(gneg) + i, make_float4(-g.x, -g.y, -g.z, -g.w));
+    }
+}
+__global__ void step_bwd_scalar_kernel(const float *__restrict__ lw, const float *__restrict__ lse,
+                                       const float *__restrict__ glw, const float *__restrict__ glse, int64_t n,
+                                       int K, float *__restrict__ gpos, float *__restrict__ gneg)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t row = i / K;
+        float g = glw ? glw[i] : 0.f;
+        if (glse) g = fmaf(glse[row], expf(lw[i] - lse[row]), g);
+        gpos[i] = g;
+        if (gneg) gneg[i] = -g;
+    }
+}
+
+__global__ void is_accumulate_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                     const float *__restrict__ c, float *__restrict__ acc,
+                                     float *__restrict__ lw, int64_t n, int first)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = a[i];
+        if (b) v = __fadd_rn(v, b[i]);
+        if (c) v = __fsub_rn(v, c[i]);
+        if (lw) lw[i] = v;
+        acc[i] = first ? v : __fadd_rn(acc[i], v);
+    }
+}
+
+// mean[b,d] = sum_k softmax(lw)[b,k] x[b,k,d]; second[b,d] likewise with x^2.  One CTA per row,
+// d processed in chunks of 8 register accumulators.
+__global__ void weighted_moments_kernel(const float *__restrict__ x, const float *__restrict__ lw, int B, int K,
+                                        int D, float *__restrict__ mean, float *__restrict__ second)
+{
+    __shared__ float scratch[32];
+    for (int row = blockIdx.x; row < B; row += gridDim.x) {
+        const float *r = lw + (size_t)row * K;
+        const float *xr = x + (size_t)row * K * D;
+        int bad;
+        const float m = row_max(r, K, scratch, &bad);
+        float s = 0.f;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) s += expf(r[k] - m);
+        s = block_allreduce(s, 0.f, OpSumF(), scratch);
+        const float lse = bad ? NAN : m + logf(s);
+        for (int d0 = 0; d0 < D; d0 += 8) {
+            float a1[8], a2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { a1[q] = 0.f; a2[q] = 0.f; }
+            const int nd = min(8, D - d0);
+            for (int k = threadIdx.x; k < K; k += blockDim.x) {
+                const float w = expf(r[k] - lse);
+                const float *xp = xr + (size_t)k * D + d0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < nd) { const float v = xp[q]; a1[q] = fmaf(w, v, a1[q]); a2[q] = fmaf(w * v, v, a2[q]); }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float t1 = block_allreduce(a1[q], 0.f, OpSumF(), scratch);
+                const float t2 = block_allreduce(a2[q], 0.f, OpSumF(), scratch);
+                if (threadIdx.x == 0 && q < nd) {
+                    mean[(size_t)row * D + d0 + q] = t1;
+                    if (second) second[(size_t)row * D + d0 + q] = t2;
+                }
+            }
+        }
+    }
+}
+
+static int row_threads(int64_t K) { return K >= 4096 ? 256 : (K >= 1024 ? 128 : (K >= 128 ? 64 : 32)); }
+static unsigned row_grid(int64_t B, int threads)
+{
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t cap = (int64_t)sms * (2048 / threads);
+    return (unsigned)(B < cap ? B : cap);
+}
+static unsigned flat_grid(int64_t n, int threads)
+{
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+int launch_logsumexp_f32(const float *lw, int64_t B, int64_t K, float *lse, int32_t *flags, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    logsumexp_rows_kernel<float><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, lse, flags);
+    count_launch();
+    return check_launch("logsumexp_rows_kernel<float>");
+}
+int launch_logsumexp_f64(const double *lw, int64_t B, int64_t K, double *lse, int32_t *flags, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    logsumexp_rows_kernel<double><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, lse, flags);
+    count_launch();
+    return check_launch("logsumexp_rows_kernel<double>");
+}
+int launch_lognormexp_f32(const float *lw, int64_t B, int64_t K, float *out, int exponentiate, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    lognormexp_kernel<<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, out, exponentiate);
+    count_launch();
+    return check_launch("lognormexp_kernel");
+}
+int launch_log_ess_f32(const float *lw, int64_t B, int64_t K, float *out, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    log_ess_kernel<float><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, out);
+    count_launch();
+    return check_launch("log_ess_kernel<float>");
+}
+int launch_log_ess_f64(const double *lw, int64_t B, int64_t K, double *out, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    log_ess_kernel<double><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, out);
+    count_launch();
+    return check_launch("log_ess_kernel<double>");
+}
+int launch_step_bwd_f32(const float *lw, const float *lse, const float *glw, const float *glse, int64_t B,
+                        int64_t K, float *gpos, float *gneg, cudaStream_t st)
+{
+    const int64_t n = B * K;
+    auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if ((K & 3) == 0 && aligned(lw) && aligned(glw) && aligned(gpos) && aligned(gneg)) {
+        step_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, st>>>(lw, lse, glw, glse, n / 4, (int)K, gpos, gneg);
+    } else {
+        step_bwd_scalar_kernel<<<flat_grid(n, 256), 256, 0, st>>>(lw, lse, glw, glse, n, (int)K, gpos, gneg);
+    }
+    count_launch();
+    return check_launch("step_bwd_kernel");
+}
+int launch_is_accumulate_f32(const float *a, const float *b, const float *c, float *acc, float *lw, int64_t n,
+                             int first, cudaStream_t st)
+{
+    is_accumulate_kernel<<<flat_grid(n, 256), 256, 0, st>>>(a, b, c, acc, lw, n, first);
+    count_launch();
+    return check_launch("is_accumulate_kernel");
+}
+int launch_weighted_moments_f32(const float *x, const float *lw, int64_t B, int64_t K, int64_t D, float *mean,
+                                float *second, cudaStream_t st)
+{
+    const int t = row_threads(K);
+    weighted_moments_kernel<<<row_grid(B, t), t, 0, st>>>(x, lw, (int)B, (int)K, (int)D, mean, second);
+    count_launch();
+    return check_launch("weighted_moments_kernel");
+}
+
+} // namespace aesmc

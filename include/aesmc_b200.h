@@ -1,0 +1,139 @@
+/*
+ * aesmc_b200.h -- C ABI of libaesmc_b200.so: the sm_100a implementation of aesmc's SMC hot path.
+ *
+ * The reference (tuananhle7/aesmc) has no FFI; its boundary is the Python API of
+ * aesmc/inference.py, aesmc/state.py, aesmc/math.py, aesmc/statistics.py.  Each
+ * entry point below is what a binding for that path calls, and cites the reference lines it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all tensors are dense,
+ *     row-major: particle tables are [B, K] (row = independent SMC problem, column = particle),
+ *     particle state is [B, K, D]
+ *   - sizes are int64_t; `stream` is a cudaStream_t passed as void*; functions only enqueue work on
+ *     that stream, never synchronise, own no memory and keep no state between calls (re-entrant)
+ *   - return value: AESMC_OK or an AESMC_ERR_* code; aesmc_last_error_string() describes the last
+ *     failure on the calling thread
+ *   - data-dependent conditions (NaN weights, degenerate rows) are reported asynchronously by
+ *     OR-ing AESMC_FLAG_* bits into the caller-provided int32 `flags` word
+ */
+#ifndef AESMC_B200_H
+#define AESMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AESMC_OK 0
+#define AESMC_ERR_BAD_ARG 1     /* null/negative/misaligned argument              -> ValueError   */
+#define AESMC_ERR_LAUNCH 2      /* cudaGetLastError() after launch                -> RuntimeError */
+#define AESMC_ERR_UNSUPPORTED 3 /* shape outside what this build handles          -> RuntimeError */
+
+/* bits OR-ed into *flags by kernels */
+#define AESMC_FLAG_NAN 1        /* a log-weight is NaN: inference.py:244-245 FloatingPointError   */
+#define AESMC_FLAG_DEGENERATE 2 /* a row's normaliser is not finite and positive (all -inf, +inf):
+                                   the reference silently emits index K there         */
+#define AESMC_FLAG_INDEX_RANGE 4 /* an ancestor index outside [0, K) was passed to a gather       */
+
+/* resampling arithmetic */
+#define AESMC_MODE_EXACT 0 /* reference-order arithmetic: numpy float32 exp, scipy logsumexp's
+                              pairwise sums, sequential float32 cumulative sum, float64 comparison;
+                              ancestor indices are bit-identical to the reference's              */
+#define AESMC_MODE_FAST 1  /* warp-shuffle reductions, ex2.approx, parallel block scan; indices may
+                              differ from the reference where a position is within rounding of a
+                              CDF boundary                                                        */
+
+int aesmc_version(void);
+const char *aesmc_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t aesmc_launch_count(void);
+/* largest K the single-CTA-per-row step kernel accepts (shared-memory bound) */
+int64_t aesmc_max_particles_single_cta(void);
+
+/*
+ * One SMC time step over B independent rows of K particles.
+ * Replaces: log-weight formation           inference.py:97-98, 125-126   (log_w = (a + b) - c)
+ *           per-step log-evidence term     inference.py:130              (lse[b] = logsumexp_k log_w)
+ *           sample_ancestral_index         inference.py:234-269, math.py:6-51
+ *           state.resample of the newest latent   state.py:158-183 via inference.py:102-104
+ *
+ *   lp_a [B,K]; lp_b, lp_c [B,K] or NULL (treated as 0)
+ *   u    [B] float64 uniforms in [0,1), one per row (inference.py:250); NULL iff idx == NULL
+ *   log_w [B,K] out (must not alias the inputs); lse [B] out or NULL
+ *   idx  [B,K] int32 out, or NULL to skip resampling (last time step / importance sampling)
+ *   x_in [B,K,D] -> x_out [B,K,D] = x_in[b, idx[b,k], :] (fused ancestral gather); both NULL to skip
+ *   flags: int32[1], OR-ed with AESMC_FLAG_*
+ */
+int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u,
+                       int64_t B, int64_t K, float *log_w, float *lse, int32_t *idx,
+                       const float *x_in, float *x_out, int64_t D, int32_t *flags, int mode,
+                       void *stream);
+
+/*
+ * Resampling entered at a later stage (used by the staged parity tests, and useful on their own):
+ *   from normalised weights w [B,K]: cumulative sum (inference.py:257), renormalisation by the last
+ *   entry (:260-261), search (:263-264);  from a normalised CDF [B,K]: the search alone.
+ */
+int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,
+                                    int32_t *flags, int mode, void *stream);
+int aesmc_resample_from_cdf_f32(const float *cdf, const double *u, int64_t B, int64_t K, int32_t *idx,
+                                int32_t *flags, void *stream);
+
+/* Importance-sampling accumulation (inference.py:156-157): acc += (a + b) - c elementwise over n
+ * floats; log_w (nullable) receives the per-step term. */
+int aesmc_is_accumulate_f32(const float *lp_a, const float *lp_b, const float *lp_c, float *acc,
+                            float *log_w, int64_t n, int first, void *stream);
+
+/* Row-wise logsumexp over particles (inference.py:130,158; statistics.py:90): lse[b]. */
+int aesmc_logsumexp_f32(const float *log_w, int64_t B, int64_t K, float *lse, int32_t *flags, void *stream);
+int aesmc_logsumexp_f64(const double *log_w, int64_t B, int64_t K, double *lse, int32_t *flags, void *stream);
+
+/* Autograd of the step's log-weight/log-evidence outputs:
+ *   g[b,k] = g_log_w[b,k] (nullable) + g_lse[b] (nullable) * exp(log_w[b,k] - lse[b])
+ * written to g_pos (gradient of lp_a and lp_b) and, if non-NULL, -g to g_neg (gradient of lp_c). */
+int aesmc_step_bwd_f32(const float *log_w, const float *lse, const float *g_log_w, const float *g_lse,
+                       int64_t B, int64_t K, float *g_pos, float *g_neg, void *stream);
+
+/* lognormexp / exponentiate_and_normalize over the last axis (math.py:6-51, torch branch):
+ * out[b,k] = log_w[b,k] - lse[b]   (exponentiate == 0)   or   exp(log_w[b,k] - lse[b]). */
+int aesmc_lognormexp_f32(const float *log_w, int64_t B, int64_t K, float *out, int exponentiate, void *stream);
+
+/* Ancestral gather, any element type (state.py:158-183): dst[b,k,:] = src[b, idx[b,k], :] where a
+ * particle is `row_bytes` contiguous bytes.  idx is int32 (idx_is_i64 == 0) or int64. */
+int aesmc_gather_bytes(const void *src, const void *idx, int idx_is_i64, int64_t B, int64_t K,
+                       int64_t row_bytes, void *dst, int32_t *flags, void *stream);
+
+/* Backward of the gather (autograd of torch.gather = scatter_add, state.py:179):
+ * gsrc[b,j,:] = sum_{k : idx[b,k]==j} gdst[b,k,:].  gsrc is fully written (zeros where no child).
+ * sorted != 0: the caller guarantees every idx row is non-decreasing (true for indices produced by
+ * aesmc_smc_step_f32); children are then summed run by run in k order, deterministically and
+ * without atomics.  sorted == 0: atomic scatter-add, any index pattern. */
+int aesmc_gather_bwd_f32(const float *gdst, const void *idx, int idx_is_i64, int64_t B, int64_t K,
+                         int64_t D, float *gsrc, int sorted, void *stream);
+int aesmc_gather_bwd_f64(const double *gdst, const void *idx, int idx_is_i64, int64_t B, int64_t K,
+                         int64_t D, double *gsrc, int sorted, void *stream);
+
+/* Genealogy composition (inference.py:226-229): out[b,k] = prev[b, cur[b,k]]; int32. */
+int aesmc_compose_index_i32(const int32_t *prev, const int32_t *cur, int64_t B, int64_t K,
+                            int32_t *out, void *stream);
+/* out[b,k] = k (inference.py:215-220) */
+int aesmc_iota_index_i32(int64_t B, int64_t K, int32_t *out, void *stream);
+/* int32 <-> int64 index conversion for the LongTensor API surface (inference.py:266-269) */
+int aesmc_index_widen(const int32_t *in, int64_t *out, int64_t n, void *stream);
+int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream);
+
+/* statistics.log_ess (statistics.py:79-91): 2*lse(lw) - lse(2*lw) per row. */
+int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream);
+int aesmc_log_ess_f64(const double *log_w, int64_t B, int64_t K, double *out, void *stream);
+
+/* statistics.empirical_mean / empirical_variance fast path (statistics.py:7-76 with f = x, x^2):
+ * mean[b,d] = sum_k w[b,k] x[b,k,d], second[b,d] = sum_k w[b,k] x[b,k,d]^2, w = softmax_k(log_w). */
+int aesmc_weighted_moments_f32(const float *x, const float *log_w, int64_t B, int64_t K, int64_t D,
+                               float *mean, float *second, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AESMC_B200_H */
