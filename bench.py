@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- SMC hot-path throughput on B200 (BASELINE.json metric: particle-steps/s = B*K*T / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [--steps K] [--warmup W]       # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU, weak scaling
+
+Workload (BASELINE config 2): B = 4096 independent rows x K = 4096 particles x T = 100 time steps,
+scalar latent (D = 1), float32.  One bench "step" = one full pass of the hot path over the T time steps:
+    value  T launches of the fused step kernel (log-weights, logsumexp, systematic resampling, ancestral
+           gather) + the log-evidence reduction, on synthetic log-prob tensors already resident in HBM
+           (a ring of 4 x 192 MiB input sets, larger than the 126 MB L2, so nothing is served from cache)
+    e2e    aesmc_b200.inference.infer('smc', ...) -- the public API a user calls -- on the bootstrap-filter
+           LGSSM user model (torch eager), with the observations [T,B] in pinned HOST memory copied H2D
+           inside the timed region and the log-evidence [B] copied back D2H
+Rows are independent SMC problems, so ranks shard the batch axis with no data-path collective
+("scaling": "weak": every rank processes B rows).
+"""
+import argparse
+import json
+import math
+import os
+import statistics as pystats
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ROWS, K_PARTICLES, T_STEPS, D_LATENT = 4096, 4096, 100, 1
+RING = 4
+METRIC = "smc_particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": pystats.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(seconds, world, dev):
+    if world == 1:
+        return seconds
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------
+def run_native(args):
+    import __graft_entry__ as graft
+    graft.build()
+    from aesmc_b200 import _lib, _ops, inference
+    from tests.models import lgssm
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    B, K, T, D = args.batch, args.particles, args.timesteps, D_LATENT
+    mode = args.mode
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    # ---- synthetic inputs resident in HBM (SURVEY 8d core microbench) ----------------------------
+    ring = [[torch.randn(B, K, device=dev, generator=gen) - 1.4 for _ in range(3)] for _ in range(RING)]
+    arena = [torch.randn(B, K, device=dev, generator=gen), torch.empty(B, K, device=dev)]
+    u = torch.rand(T - 1, B, dtype=torch.float64, device=dev, generator=gen)
+    log_w = torch.empty(T, B, K, device=dev)
+    idx = torch.empty(max(T - 1, 1), B, K, dtype=torch.int32, device=dev)
+    lse = torch.empty(T, B, device=dev)
+    flags = _ops.new_flags(dev)
+    mode_code = _ops.mode_code(mode)
+    stream = torch.cuda.current_stream()
+    logK = math.log(K)
+
+    def core_pass(events=None):
+        for t in range(T):
+            a, b, c = ring[t % RING]
+            last = t == T - 1
+            if events is not None:
+                events[t].record(stream)
+            _lib.call("aesmc_smc_step_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(),
+                      None if last else u[t].data_ptr(), B, K, log_w[t].data_ptr(), lse[t].data_ptr(),
+                      None if last else idx[t].data_ptr(), None if last else arena[t & 1].data_ptr(),
+                      None if last else arena[(t + 1) & 1].data_ptr(), D, flags.data_ptr(), mode_code)
+        if events is not None:
+            events[T].record(stream)
+        return (lse - logK).sum(dim=0)  # inference.py:130-132
+
+    for _ in range(args.warmup):
+        lml = core_pass()
+    barrier_sync(world)
+    launches0 = _lib.launch_count()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(T + 1)] for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        start.record(stream)
+        for s in range(args.steps):
+            lml = core_pass(events[s])
+        stop.record(stream)
+        barrier_sync(world)
+    launches = _lib.launch_count() - launches0
+    seconds = max_over_ranks(start.elapsed_time(stop) / 1e3, world, dev)
+    assert int(flags.item()) == 0 and bool(torch.isfinite(lml).all())
+    ms_per_step = seconds * 1e3 / args.steps
+    value = world * B * K * T / (seconds / args.steps)
+
+    # dominant kernel: per-launch duration from the event pairs inside the timed region
+    durs = [events[s][t].elapsed_time(events[s][t + 1]) for s in range(args.steps) for t in range(T - 1)]
+    kernel_ms = sum(durs) / len(durs)
+    bytes_per_launch = (20 + 8 * D) * B * K
+    peak, peak_src = load_peaks()
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("smc_step_kernel_%s" % mode)
+    roofline = {"bound": "hbm", "kernel": "smc_step_kernel<%s>" % mode, "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "bytes_per_launch": bytes_per_launch, "launch_ms": round(kernel_ms, 4), "peak_source": peak_src}
+
+    # ---- e2e: public infer() with host observation buffers -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ys = lgssm.simulate(T, B, seed=100 + rank)
+        obs_host = torch.from_numpy(ys).pin_memory()
+        u_host = torch.from_numpy(np.random.default_rng(7 + rank).random((T - 1, B))).pin_memory()
+        out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        models = lgssm.bootstrap_filter(device=dev)
+        del log_w, idx
+        torch.cuda.empty_cache()
+
+        def e2e_pass():
+            obs = obs_host.to(dev, non_blocking=True)
+            uu = u_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                res = inference.infer("smc", obs, *models, K, return_log_marginal_likelihood=True,
+                                      return_latents=False, return_log_weight=False, uniforms=uu,
+                                      resampling_mode=mode)
+            out_host.copy_(res["log_marginal_likelihood"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_pass()
+        reps = max(1, min(args.steps, 5))
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for _ in range(reps):
+            e2e_pass()
+        e_stop.record()
+        barrier_sync(world)
+        e_seconds = max(time.perf_counter() - t0, e_start.elapsed_time(e_stop) / 1e3)
+        e_seconds = max_over_ranks(e_seconds, world, dev)
+        e2e = {"value": world * B * K * T / (e_seconds / reps), "unit": UNIT,
+               "h2d_bytes_per_step": obs_host.numel() * 4 + u_host.numel() * 8, "d2h_bytes_per_step": B * 4,
+               "ms_per_step": e_seconds * 1e3 / reps, "steps": reps,
+               "api": "aesmc_b200.inference.infer('smc', bootstrap LGSSM user model in torch eager)"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample ---------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_baseline = time_oracle_core(K, T, D, args.cpu_rows)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE config 2: 1-D LGSSM-shaped SMC core, B=%d rows/GPU x K=%d particles x T=%d, D=%d"
+                                       % (B, K, T, D), "resampling_mode": mode, "parallelism": "batch rows sharded, dp%d" % world,
+                           "l2": "inputs ring %d x %d MiB > 126 MB L2; no flush needed" % (RING, 3 * B * K * 4 >> 20)},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": launches}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def time_oracle_core(K, T, D, rows):
+    """The C restatement of the reference's per-step arithmetic (oracle/smc_oracle.c), one host
+    thread, on `rows` rows of the same workload."""
+    from oracle import core as oracle
+    rng = np.random.default_rng(0)
+    a, b, c = [(rng.standard_normal((RING, rows, K)) - 1.4).astype(np.float32) for _ in range(3)]
+    x = rng.standard_normal((rows, K, D)).astype(np.float32)
+    u = rng.random((T - 1, rows))
+    t0 = time.perf_counter()
+    _, _, st = oracle.core_pass(a, b, c, u, x, T)
+    dt = time.perf_counter() - t0
+    assert st == 0
+    return {"value": rows * K * T / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/smc_oracle.c core pass, %d rows x K=%d x T=%d (%.1f s)" % (rows, K, T, dt)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU algorithm (oracle/reference_port.py) on the host cores
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import reference_port as port
+    from tests.models import lgssm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, T = args.particles, args.timesteps
+    rows = args.ref_rows
+    ys = lgssm.simulate(T, rows, seed=100)
+    obs = [torch.from_numpy(y) for y in ys]
+    models = lgssm.bootstrap_filter()
+
+    def one():
+        with torch.no_grad():
+            res = port.infer("smc", obs, *models, K, return_log_marginal_likelihood=True, return_latents=False,
+                             return_log_weight=False)
+        return res["log_marginal_likelihood"]
+
+    for _ in range(min(args.warmup, 1)):
+        one()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    value = rows * K * T / sec
+    sample = "oracle/reference_port.infer('smc') bootstrap LGSSM, %d rows x K=%d x T=%d per step" % (rows, K, T)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2 shape (K=%d, T=%d) on a bounded sample of %d rows" % (K, T, rows)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--batch", type=int, default=B_ROWS)
+    ap.add_argument("--particles", type=int, default=K_PARTICLES)
+    ap.add_argument("--timesteps", type=int, default=T_STEPS)
+    ap.add_argument("--cpu-rows", type=int, default=256)
+    ap.add_argument("--ref-rows", type=int, default=64)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,9 +74,13 @@ class Proposal(nn.Module):
 
 
 # ---- bootstrap particle filter on a fixed scalar LGSSM (no learnable parameters) ------------------
+def _scalar(v, device):
+    return torch.tensor(float(v), device=device)
+
+
 class BootstrapInitial:
-    def __init__(self, mean, variance):
-        self.mean, self.std = mean, math.sqrt(variance)
+    def __init__(self, mean, variance, device=None):
+        self.mean, self.std = _scalar(mean, device), _scalar(math.sqrt(variance), device)
 
     def __call__(self):
         return Normal(loc=self.mean, scale=self.std)
@@ -101,8 +105,8 @@ class BootstrapEmission:
 class BootstrapProposal:
     """Proposal == prior dynamics, so log-weights reduce to the emission log-density."""
 
-    def __init__(self, initial_mean, initial_variance, matrix, variance, offset=0.0):
-        self.m0, self.s0 = initial_mean, math.sqrt(initial_variance)
+    def __init__(self, initial_mean, initial_variance, matrix, variance, offset=0.0, device=None):
+        self.m0, self.s0 = _scalar(initial_mean, device), _scalar(math.sqrt(initial_variance), device)
         self.matrix, self.std, self.offset = matrix, math.sqrt(variance), offset
 
     def __call__(self, previous_latents=None, time=None, observations=None):
@@ -111,10 +115,11 @@ class BootstrapProposal:
         return Normal(loc=previous_latents[-1] * self.matrix + self.offset, scale=self.std)
 
 
-def bootstrap_filter(m0=0.0, P0=1.0, A=0.9, Q=1.0, C=1.0, R=0.25):
-    """(initial, transition, emission, proposal) of the BASELINE config-2 bootstrap filter."""
-    return (BootstrapInitial(m0, P0), BootstrapTransition(A, Q), BootstrapEmission(C, R),
-            BootstrapProposal(m0, P0, A, Q))
+def bootstrap_filter(m0=0.0, P0=1.0, A=0.9, Q=1.0, C=1.0, R=0.25, device=None):
+    """(initial, transition, emission, proposal) of the BASELINE config-2 bootstrap filter.  ``device``
+    is where the time-0 proposal draws its particles (everything downstream follows the latents)."""
+    return (BootstrapInitial(m0, P0, device), BootstrapTransition(A, Q), BootstrapEmission(C, R),
+            BootstrapProposal(m0, P0, A, Q, device=device))
 
 
 def simulate(T, B, m0=0.0, P0=1.0, A=0.9, Q=1.0, C=1.0, R=0.25, seed=0):

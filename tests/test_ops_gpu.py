@@ -1,0 +1,199 @@
+"""GPU tests of the remaining C-ABI entry points against the oracle / plain torch: gather and its
+backward, logsumexp, step backward, log_ess, weighted moments, index utilities, and the public
+math / state / statistics wrappers (including the reference's own known-answer vectors)."""
+import numpy as np
+import pytest
+import torch
+
+import aesmc_b200
+from aesmc_b200 import _ops, inference, math as amath, state, statistics
+from oracle import core as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape,dtype", [((3, 7), torch.float32), ((4, 100, 3), torch.float32),
+                                         ((2, 513, 10), torch.float32), ((2, 64, 4, 5), torch.float64),
+                                         ((3, 33, 3), torch.int64), ((2, 50, 3), torch.uint8),
+                                         ((2, 40, 5), torch.float16)])
+def test_gather_matches_torch(cuda, shape, dtype):
+    g = torch.Generator().manual_seed(1)
+    B, K = shape[:2]
+    v = (torch.randn(shape, generator=g) * 10).to(dtype).to(cuda)
+    idx = torch.randint(0, K, (B, K), generator=g).to(cuda)
+    want = torch.gather(v, 1, idx.reshape(B, K, *([1] * (v.dim() - 2))).expand_as(v))
+    assert torch.equal(state.resample(v, idx), want)
+    assert torch.equal(state.resample(v, idx.int()), want)
+    assert torch.equal(state.resample({"a": v}, idx)["a"], want)
+
+
+def test_resample_known_answers_and_cpu_staging(cuda):
+    # test/test_state.py:286-303 on CPU tensors (staged through the GPU, returned on the CPU)
+    value = torch.Tensor([[1, 2, 3], [4, 5, 6]])
+    idx = torch.LongTensor([[1, 2, 0], [0, 0, 1]])
+    out = state.resample(value, idx)
+    assert not out.is_cuda and torch.equal(out, torch.Tensor([[2, 3, 1], [4, 4, 5]]))
+    assert state.resample(torch.rand(3, 2, 4, 5), torch.zeros(3, 2).long()).shape == (3, 2, 4, 5)
+    with pytest.raises(AttributeError):
+        state.resample([1, 2], idx)
+    with pytest.raises(IndexError):
+        state.resample(value, torch.LongTensor([[1, 2, 3], [0, 0, 1]]))
+
+
+def test_genealogy_known_answer(cuda):
+    # test/test_inference.py:13-40
+    latents = [torch.Tensor([[1, 2, 3]]), torch.Tensor([[4, 5, 6]]), torch.Tensor([[7, 8, 9]]), torch.Tensor([[10, 11, 12]])]
+    anc = [torch.LongTensor([[0, 2, 1]]), torch.LongTensor([[2, 0, 0]]), torch.LongTensor([[1, 2, 0]])]
+    want = [[1, 1, 2], [4, 4, 6], [8, 9, 7], [10, 11, 12]]
+    for dev in ("cpu", cuda):
+        got = inference.get_resampled_latents([l.to(dev) for l in latents], [a.to(dev) for a in anc])
+        assert [g[0].tolist() for g in got] == want
+    rng = np.random.default_rng(0)
+    T, B, K = 6, 3, 50
+    lat = [torch.from_numpy(rng.standard_normal((B, K, 2)).astype(np.float32)).to(cuda) for _ in range(T)]
+    anc = [torch.from_numpy(np.sort(rng.integers(0, K, (B, K)), axis=1)).to(cuda) for _ in range(T - 1)]
+    got = inference.get_resampled_latents(lat, anc)
+    cur = np.tile(np.arange(K), (B, 1))
+    for t in range(T - 1, -1, -1):
+        assert np.array_equal(got[t].cpu().numpy(), oracle.resample(lat[t].cpu().numpy(), cur))
+        if t:
+            cur = oracle.compose_index(anc[t - 1].cpu().numpy(), cur)
+
+
+@pytest.mark.parametrize("sorted_rows", [True, False])
+@pytest.mark.parametrize("D", [1, 3, 10])
+def test_gather_backward(cuda, sorted_rows, D):
+    rng = np.random.default_rng(3)
+    B, K = 5, 700
+    idx = rng.integers(0, K, (B, K))
+    if sorted_rows:
+        idx = np.sort(idx, axis=1)
+        idx[0] = 17                               # one parent takes everything
+    x = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda).requires_grad_()
+    g = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda)
+    out = _ops.gather(x, torch.from_numpy(idx).int().to(cuda), sorted_rows=sorted_rows)
+    out.backward(g)
+    ref = oracle.resample_bwd(g.cpu().numpy(), idx)
+    if sorted_rows:   # run-ordered summation == the reference's CPU scatter_add order
+        assert np.array_equal(x.grad.cpu().numpy(), ref)
+    else:
+        np.testing.assert_allclose(x.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_step_backward_matches_torch_autograd(cuda):
+    gen = torch.Generator(device=cuda).manual_seed(2)
+    B, K, D = 6, 1000, 3
+    leaves = [torch.randn(B, K, device=cuda, generator=gen).requires_grad_() for _ in range(3)]
+    x = torch.randn(B, K, D, device=cuda, generator=gen).requires_grad_()
+    u = torch.rand(B, dtype=torch.float64, device=cuda, generator=gen)
+    flags = _ops.new_flags(cuda)
+    log_w, lse, idx, xr = _ops.smc_step(*leaves, u, x, flags, "exact", True)
+    cot = [torch.randn_like(log_w), torch.randn_like(lse), torch.randn_like(xr)]
+    (log_w * cot[0]).sum().add((lse * cot[1]).sum()).add((xr * cot[2]).sum()).backward()
+    got = [t.grad.clone() for t in leaves + [x]]
+    for t in leaves + [x]:
+        t.grad = None
+    lw2 = (leaves[0] + leaves[1]) - leaves[2]
+    lse2 = torch.logsumexp(lw2, dim=1)
+    xr2 = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(B, K, D))
+    (lw2 * cot[0]).sum().add((lse2 * cot[1]).sum()).add((xr2 * cot[2]).sum()).backward()
+    for mine, t in zip(got, leaves + [x]):
+        torch.testing.assert_close(mine, t.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_logsumexp_and_log_ess(cuda, golden):
+    g = golden["default"]
+    lw = torch.from_numpy(g["stats/lw"]).to(cuda)
+    np.testing.assert_allclose(statistics.log_ess(lw).cpu().numpy(), g["stats/log_ess"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(statistics.ess(lw).cpu().numpy(), g["stats/ess"], rtol=1e-5)
+    rng = np.random.default_rng(0)
+    for B, K in ((1, 1), (3, 5), (40, 1000), (7, 5000)):
+        a = (rng.standard_normal((B, K)) * 4).astype(np.float32)
+        np.testing.assert_allclose(_ops.logsumexp_rows(torch.from_numpy(a).to(cuda)).cpu().numpy(), oracle.lse_f64(a), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(statistics.log_ess(torch.from_numpy(a).to(cuda)).cpu().numpy(), oracle.log_ess_f64(a), rtol=1e-5, atol=1e-5)
+    # shapes: test/test_statistics.py:46-69
+    assert statistics.log_ess(-torch.rand(2, 3)).shape == (2,)
+    assert statistics.log_ess(-torch.rand(3, 1)).shape == (3,)
+    assert statistics.log_ess(-torch.rand(3)).shape == ()
+    # float64 with +-1e6 offsets: test/test_statistics.py:71-115
+    nw = np.array([0.2, 0.3, 0.5])
+    for shift in (np.log(0.47), 1e6, -1e6):
+        lw64 = torch.from_numpy(np.log(nw) + shift)
+        assert abs(statistics.log_ess(lw64).item() - np.log(1 / np.sum(nw ** 2))) < 1e-7
+        assert abs(statistics.ess(lw64.to(cuda)).item() - 1 / np.sum(nw ** 2)) < 1e-7
+    # differentiable path
+    t = torch.randn(4, 50, device=cuda, requires_grad=True)
+    statistics.log_ess(t).sum().backward()
+    t2 = t.detach().clone().requires_grad_()
+    (2 * torch.logsumexp(t2, 1) - torch.logsumexp(2 * t2, 1)).sum().backward()
+    torch.testing.assert_close(t.grad, t2.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_math_surface(cuda):
+    # shapes / dims / type preservation: test/test_math.py:9-49
+    for values in (torch.rand(2, 3, 4, 5), np.random.rand(2, 3, 4, 5)):
+        for fn in (amath.lognormexp, amath.exponentiate_and_normalize):
+            out = fn(values, dim=2)
+            assert type(out) is type(values) and tuple(out.shape) == (2, 3, 4, 5)
+    x = torch.Tensor([1, 2, 3])
+    want = torch.exp(x) / torch.exp(x).sum()
+    np.testing.assert_allclose(amath.lognormexp(x).numpy(), torch.log(want).numpy(), atol=1e-6)
+    np.testing.assert_allclose(amath.exponentiate_and_normalize(x).numpy(), want.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(amath.exponentiate_and_normalize(np.array([1., 2., 3.])),
+                               np.exp([1., 2., 3.]) / np.exp([1., 2., 3.]).sum(), rtol=1e-7)
+    v = torch.randn(5, 6, 7, device=cuda)
+    torch.testing.assert_close(amath.lognormexp(v, dim=1), v - torch.logsumexp(v, 1, keepdim=True), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(amath.exponentiate_and_normalize(v, dim=0), torch.softmax(v, 0), rtol=1e-5, atol=1e-7)
+    r = torch.randn(3, 9, device=cuda, requires_grad=True)
+    amath.lognormexp(r, dim=1)[:, 0].sum().backward()
+    r2 = r.detach().clone().requires_grad_()
+    torch.log_softmax(r2, 1)[:, 0].sum().backward()
+    torch.testing.assert_close(r.grad, r2.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_statistics_moments(cuda, golden):
+    g = golden["default"]
+    lw, val = torch.from_numpy(g["stats/lw"]), torch.from_numpy(g["stats/value"])
+    for dev in ("cpu", cuda):
+        np.testing.assert_allclose(statistics.empirical_mean(val.to(dev), lw.to(dev)).cpu().numpy(), g["stats/mean"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(statistics.empirical_variance(val.to(dev), lw.to(dev)).cpu().numpy(), g["stats/var"], rtol=1e-4, atol=1e-5)
+    # general f keeps the reference's particle loop: test/test_statistics.py:9-42
+    out = statistics.empirical_expectation(torch.rand(2, 3, 4, 5, 6), -torch.rand(2, 3), lambda a: torch.rand(2, 7, 8))
+    assert out.shape == (2, 7, 8)
+    value = torch.Tensor([1, 2, 3]).unsqueeze(0)
+    lw3 = torch.log(torch.Tensor([0.2, 0.3, 0.5]).unsqueeze(0))
+    got = statistics.empirical_expectation(value, lw3, lambda v: v * 2)
+    np.testing.assert_allclose(got.numpy(), [1 * 2 * 0.2 + 2 * 2 * 0.3 + 3 * 2 * 0.5], rtol=1e-6)
+    # scalar latents [B,K]
+    x = torch.randn(6, 300, device=cuda)
+    w = torch.randn(6, 300, device=cuda)
+    torch.testing.assert_close(statistics.empirical_mean(x, w), (torch.softmax(w, 1) * x).sum(1), rtol=1e-5, atol=1e-6)
+
+
+def test_sample_ancestral_index_surface(cuda):
+    # test/test_inference.py:44-84
+    for shape in ((2, 3), (1, 2), (2, 1)):
+        assert inference.sample_ancestral_index(torch.rand(*shape)).size() == torch.Size(shape)
+    out = inference.sample_ancestral_index(torch.rand(1, 1))
+    assert out.dtype == torch.int64 and not out.is_cuda
+    assert inference.sample_ancestral_index(torch.rand(2, 5, device=cuda)).is_cuda
+    weight = [0.2, 0.3, 0.5]
+    idx = inference.sample_ancestral_index(torch.log(torch.Tensor(weight)).unsqueeze(0).expand(10000, 3))
+    freq = np.bincount(idx.numpy().ravel(), minlength=3) / idx.numel()
+    np.testing.assert_allclose(freq, weight, atol=1e-2)
+    with pytest.raises(FloatingPointError):
+        inference.sample_ancestral_index(torch.Tensor([[0.0, float("nan")]]))
+    # same numpy seed -> same draws as the reference's np.random.uniform(size=[B,1])
+    lw = torch.randn(7, 50)
+    np.random.seed(5)
+    a = inference.sample_ancestral_index(lw)
+    np.random.seed(5)
+    u = np.random.uniform(size=[7, 1])
+    ref, _ = oracle.sample_ancestral_index(lw.numpy(), u)
+    assert np.array_equal(a.numpy(), ref)
+
+
+def test_index_utils(cuda):
+    i = torch.randint(0, 1000, (5, 77), device=cuda)
+    assert torch.equal(_ops.widen_index(_ops.narrow_index(i)), i)
+    assert torch.equal(_ops.iota_index(3, 9, cuda).long(), torch.arange(9, device=cuda).expand(3, 9))

@@ -1,0 +1,218 @@
+"""Parity of the fused step kernel with the oracle (GPU; calls go through the C ABI via aesmc_b200._ops).
+
+Staged contract:
+  S1  search on an injected reference CDF                 -> 0 mismatches
+  S2  cumulative sum + search on injected weights          -> 0 mismatches (exact), counted (fast)
+  S3  full step from log-weights                           -> 0 mismatches vs the libm-log1p variant of
+      the reference ("avx2" golden) and vs the oracle; vs the SVML variant ("default") mismatches are
+      counted and must lie in rows whose scipy lse differs between the two numpy dispatch paths
+Bar: ancestor indices, log-weights and exact-mode lse bit-exact; fast-mode lse within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from aesmc_b200 import _ops, _lib
+from oracle import core as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_f32(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+
+
+def dev_f64(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(cuda)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def step_names(g):
+    return sorted({k.split("/")[1] for k in g.files if k.startswith("step/")})
+
+
+def single_cta_cases(g):
+    kmax = _lib.max_particles_single_cta()
+    return [n for n in step_names(g) if g["step/%s/lw" % n].shape[1] <= kmax]
+
+
+def run_step(lw, u, cuda, mode="exact", b=None, c=None, x=None):
+    flags = _ops.new_flags(cuda)
+    out = _ops.smc_step(dev_f32(lw, cuda), None if b is None else dev_f32(b, cuda),
+                        None if c is None else dev_f32(c, cuda), dev_f64(u, cuda),
+                        None if x is None else dev_f32(x, cuda), flags, mode, True)
+    torch.cuda.synchronize()
+    return out, int(flags.item())
+
+
+def test_s1_search_on_injected_cdf(cuda, golden):
+    g = golden["avx2"]
+    for name in single_cta_cases(g):
+        lw, u, idx = (g["step/%s/%s" % (name, k)] for k in ("lw", "u", "idx"))
+        _, _, _, _, cdf = oracle.sample_ancestral_index(lw, u, return_parts=True)
+        flags = _ops.new_flags(cuda)
+        got = _ops.resample_from_cdf(dev_f32(cdf, cuda), dev_f64(u, cuda), flags).cpu().numpy()
+        assert np.array_equal(got, idx), name
+
+
+def test_s2_scan_and_search_on_injected_weights(cuda, golden):
+    g = golden["avx2"]
+    fast_mismatch = 0
+    total = 0
+    for name in single_cta_cases(g):
+        lw, u, idx = (g["step/%s/%s" % (name, k)] for k in ("lw", "u", "idx"))
+        _, _, _, w, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+        flags = _ops.new_flags(cuda)
+        got = _ops.resample_from_weights(dev_f32(w, cuda), dev_f64(u, cuda), flags, "exact").cpu().numpy()
+        assert np.array_equal(got, idx), name
+        fast = _ops.resample_from_weights(dev_f32(w, cuda), dev_f64(u, cuda), flags, "fast").cpu().numpy()
+        fast_mismatch += int((fast != idx).sum())
+        total += idx.size
+        assert np.abs(fast.astype(np.int64) - idx).max() <= max(2, idx.shape[1] // 500), name
+    assert fast_mismatch / total < 5e-3
+    print("S2 fast-mode mismatches: %d of %d (%.2e)" % (fast_mismatch, total, fast_mismatch / total))
+
+
+def test_s3_full_step_vs_golden_libm_variant(cuda, golden):
+    g = golden["avx2"]
+    total = 0
+    for name in single_cta_cases(g):
+        lw, u, idx, lse = (g["step/%s/%s" % (name, k)] for k in ("lw", "u", "idx", "lse"))
+        (log_w, my_lse, my_idx, _), fl = run_step(lw, u, cuda)
+        assert fl == 0
+        assert np.array_equal(bits(log_w.cpu().numpy()), bits(lw)), name
+        assert np.array_equal(my_idx.cpu().numpy(), idx), name
+        assert np.array_equal(bits(my_lse.cpu().numpy()), bits(lse)), name
+        total += idx.size
+    assert total > 100000
+
+
+def test_s3_full_step_vs_golden_default_variant_counted(cuda, golden):
+    g, g2 = golden["default"], golden["avx2"]
+    mism = 0
+    total = 0
+    for name in single_cta_cases(g):
+        lw, u, idx, lse = (g["step/%s/%s" % (name, k)] for k in ("lw", "u", "idx", "lse"))
+        (_, _, my_idx, _), _ = run_step(lw, u, cuda)
+        bad_rows = np.nonzero((my_idx.cpu().numpy() != idx).any(axis=1))[0]
+        svml_rows = np.nonzero(bits(lse) != bits(g2["step/%s/lse" % name]))[0]
+        assert set(bad_rows) <= set(svml_rows), name  # disagreement only where the reference's own lse is host-dependent
+        mism += int((my_idx.cpu().numpy() != idx).sum())
+        total += idx.size
+    print("S3 vs SVML-variant reference: %d of %d indices differ" % (mism, total))
+    assert mism / total < 1e-4
+
+
+@pytest.mark.parametrize("B,K,D", [(3, 1, 1), (3, 2, 2), (5, 3, 1), (4, 31, 3), (4, 32, 1), (4, 33, 5), (7, 100, 1),
+                                   (16, 1000, 10), (9, 1023, 1), (8, 2048, 4), (6, 4096, 1), (5, 4097, 3),
+                                   (3, 8192, 1), (2, 12000, 2), (2, 16384, 1), (1, 27000, 1)])
+def test_s3_random_inputs_vs_oracle(cuda, B, K, D):
+    rng = np.random.default_rng(B * 100003 + K)
+    a, b, c = [(rng.standard_normal((B, K)) * 1.5 - 1.4).astype(np.float32) for _ in range(3)]
+    x = rng.standard_normal((B, K, D)).astype(np.float32)
+    u = rng.random(B)
+    (log_w, lse, idx, xr), fl = run_step(a, u, cuda, b=b, c=c, x=x if D > 1 else x[..., 0])
+    lw_ref = oracle.log_weight(a, b, c)
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw_ref, u, return_parts=True)
+    assert fl == 0 and st == 0
+    assert np.array_equal(bits(log_w.cpu().numpy()), bits(lw_ref))
+    assert np.array_equal(idx.cpu().numpy(), idx_ref.astype(np.int32))
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+    xr_ref = oracle.resample(x, idx_ref)
+    assert np.array_equal(xr.cpu().numpy().reshape(B, K, D), xr_ref)
+
+
+def test_heavy_tail_and_edge_rows(cuda):
+    rng = np.random.default_rng(7)
+    B, K = 12, 3000
+    lw = (rng.standard_normal((B, K)) * 8).astype(np.float32)
+    lw[0] = -0.5                       # all equal: m = K maxima
+    lw[1, 1:] = -np.inf                # single survivor
+    lw[2, ::2] = -np.inf
+    lw[3] = np.sort(lw[3])             # increasing
+    lw[4] = np.sort(lw[4])[::-1]       # decreasing
+    lw[5] += 80                        # large positive values
+    lw[6] -= 95                        # tiny weights, denormal exps
+    lw[7, :10] = lw[7].max()           # tied maxima
+    u = rng.random(B)
+    u[8] = 0.0
+    u[9] = np.nextafter(1.0, 0.0)
+    (_, lse, idx, _), fl = run_step(lw, u, cuda)
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+    assert fl == 0 and st == 0
+    assert np.array_equal(idx.cpu().numpy(), np.minimum(idx_ref, K - 1).astype(np.int32))
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+
+
+def test_fast_mode_close_to_reference(cuda):
+    rng = np.random.default_rng(11)
+    B, K = 64, 4096
+    lw = (rng.standard_normal((B, K)) - 1.4).astype(np.float32)
+    u = rng.random(B)
+    (log_w, lse, idx, _), fl = run_step(lw, u, cuda, mode="fast")
+    idx_ref, _, _, w, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+    got = idx.cpu().numpy().astype(np.int64)
+    frac = (got != idx_ref).mean()
+    print("fast-mode index mismatch fraction at K=4096: %.3e, max |d| = %d" % (frac, np.abs(got - idx_ref).max()))
+    assert frac < 5e-3 and np.abs(got - idx_ref).max() <= 2
+    np.testing.assert_allclose(lse.cpu().numpy(), oracle.lse_f64(lw), rtol=1e-6)
+    assert (np.diff(got, axis=1) >= 0).all()
+
+
+def test_flags_nan_and_degenerate(cuda):
+    lw = np.zeros((3, 64), np.float32)
+    lw[1, 5] = np.nan
+    _, fl = run_step(lw, np.full(3, 0.5), cuda)
+    assert fl & _lib.FLAG_NAN
+    lw = np.zeros((3, 64), np.float32)
+    lw[2] = -np.inf
+    (_, lse, idx, _), fl = run_step(lw, np.full(3, 0.5), cuda)
+    assert fl & _lib.FLAG_DEGENERATE and not (fl & _lib.FLAG_NAN)
+    assert np.isneginf(lse.cpu().numpy()[2])
+    assert np.array_equal(idx.cpu().numpy()[2], np.arange(64))  # identity keeps later gathers in range
+
+
+def test_no_resample_variant_and_lse_accuracy(cuda):
+    rng = np.random.default_rng(5)
+    a, b, c = [(rng.standard_normal((33, 777)) * 2).astype(np.float32) for _ in range(3)]
+    flags = _ops.new_flags(cuda)
+    log_w, lse, idx, xr = _ops.smc_step(dev_f32(a, cuda), dev_f32(b, cuda), dev_f32(c, cuda), None, None, flags,
+                                        "exact", False)
+    assert idx is None and xr is None
+    ref = oracle.log_weight(a, b, c)
+    assert np.array_equal(bits(log_w.cpu().numpy()), bits(ref))
+    np.testing.assert_allclose(lse.cpu().numpy(), oracle.lse_f64(ref), rtol=1e-6)
+
+
+def test_full_size_properties(cuda):
+    """BASELINE config-2 shape (B = K = 4096): size-independent properties of systematic resampling."""
+    B = K = 4096
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    a, b, c = [torch.randn(B, K, device=cuda, generator=gen) - 1.4 for _ in range(3)]
+    x = torch.randn(B, K, device=cuda, generator=gen)
+    u = torch.rand(B, dtype=torch.float64, device=cuda, generator=gen)
+    flags = _ops.new_flags(cuda)
+    for mode in ("exact", "fast"):
+        log_w, lse, idx, xr = _ops.smc_step(a, b, c, u, x, flags, mode, True)
+        assert int(flags.item()) == 0
+        idx = idx.long()
+        assert int(idx.min()) >= 0 and int(idx.max()) < K
+        assert bool((idx[:, 1:] >= idx[:, :-1]).all())                      # non-decreasing ancestry
+        assert torch.equal(xr, torch.gather(x, 1, idx))                      # gather is exact
+        assert torch.equal(log_w, (a + b) - c)                               # float32 (a+b)-c, bit-exact
+        w = torch.softmax(log_w.double(), dim=1)
+        counts = torch.zeros(B, K, dtype=torch.float64, device=cuda).scatter_add_(1, idx, torch.ones_like(w))
+        assert bool((counts.sum(1) == K).all())
+        # systematic resampling: offspring count is floor or ceil of K*w (up to float32 CDF rounding)
+        assert float((counts - K * w).abs().max()) < 1.0 + 1e-2
+        torch.testing.assert_close(lse.double(), torch.logsumexp(log_w.double(), 1), rtol=1e-6, atol=1e-6)
+    # a few full-size rows against the oracle, bit for bit
+    rows = [0, 1, 2047, 4095]
+    log_w, lse, idx, _ = _ops.smc_step(a, b, c, u, None, flags, "exact", True)
+    lw_rows = log_w[rows].cpu().numpy()
+    idx_ref, _, lse_ref, _, _ = oracle.sample_ancestral_index(lw_rows, u[rows].cpu().numpy(), return_parts=True)
+    assert np.array_equal(idx[rows].cpu().numpy(), idx_ref.astype(np.int32))
+    assert np.array_equal(bits(lse[rows].cpu().numpy()), bits(lse_ref))
