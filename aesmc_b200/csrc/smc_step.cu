@@ -15,13 +15,9 @@
 //       of np.digitize; the merged sequence of positions and CDF entries is never materialised)
 //   P5  coalesced store of idx, fused ancestral gather of the latent
 #include "common.cuh"
+#include "pairwise.cuh"
 
 namespace aesmc {
-
-struct PwNode { // node of numpy's pairwise-summation recursion over a row of K floats
-    int start, len, child; // child < 0: leaf; else children are nodes child, child+1
-    float val;
-};
 
 struct StepParams {
     const float *a, *b, *c;
@@ -40,83 +36,7 @@ struct StepParams {
                    // the cumulative sum); 2: `a` holds a normalised CDF (enter at the search)
 };
 
-constexpr int kMaxLevels = 40;
-
-__host__ __device__ inline int pairwise_max_nodes(int K) { return 2 * (K / 56 + 2); }
-
-// BFS construction of numpy's pairwise-sum recursion (loops_utils.h.src: n <= 128 is a leaf, else
-// split at n2 = n/2 - (n/2 % 8)).  Depends on K only; built once per CTA by thread 0.
-__device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *nlevels, int K)
-{
-    nodes[0].start = 0; nodes[0].len = K; nodes[0].child = -1; nodes[0].val = 0.f;
-    int begin = 0, end = 1, L = 0;
-    lvl_start[0] = 0;
-    while (begin < end) {
-        int cnt = end;
-        for (int i = begin; i < end; ++i) {
-            const int len = nodes[i].len, start = nodes[i].start;
-            if (len > 128) {
-                int n2 = len / 2;
-                n2 -= n2 % 8;
-                nodes[i].child = cnt;
-                nodes[cnt].start = start; nodes[cnt].len = n2; nodes[cnt].child = -1; nodes[cnt].val = 0.f;
-                ++cnt;
-                nodes[cnt].start = start + n2; nodes[cnt].len = len - n2; nodes[cnt].child = -1; nodes[cnt].val = 0.f;
-                ++cnt;
-            }
-        }
-        begin = end;
-        end = cnt;
-        lvl_start[++L] = begin;
-    }
-    *nlevels = L;
-}
-
-// Sum of buf[0..K) in numpy's pairwise order.  All threads call; result returned to all.
-__device__ float pairwise_tree_sum(const float *buf, PwNode *nodes, const int *lvl_start, int nlevels)
-{
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int nnodes = lvl_start[nlevels];
-    const int grp = tid >> 3, j = tid & 7, ngrp = NT >> 3;
-    for (int base = 0; base < nnodes; base += ngrp) { // warp-uniform trip count
-        const int n = base + grp;
-        const bool valid = (n < nnodes) && (nodes[n].child < 0);
-        int start = 0, len = 0, lim = 0;
-        float r = 0.f;
-        if (valid) {
-            start = nodes[n].start;
-            len = nodes[n].len;
-            if (len >= 8) {
-                lim = len - (len % 8);
-                r = buf[start + j];
-                for (int i = 8; i < lim; i += 8) r = __fadd_rn(r, buf[start + i + j]);
-            }
-        }
-        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 1));
-        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 2));
-        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 4));
-        if (valid && j == 0) {
-            float res;
-            if (len < 8) {
-                res = 0.f;
-                for (int i = 0; i < len; ++i) res = __fadd_rn(res, buf[start + i]);
-            } else {
-                res = r;
-                for (int i = lim; i < len; ++i) res = __fadd_rn(res, buf[start + i]);
-            }
-            nodes[n].val = res;
-        }
-    }
-    __syncthreads();
-    for (int L = nlevels - 2; L >= 0; --L) {
-        for (int n = lvl_start[L] + tid; n < lvl_start[L + 1]; n += NT) {
-            const int ch = nodes[n].child;
-            if (ch >= 0) nodes[n].val = __fadd_rn(nodes[ch].val, nodes[ch + 1].val);
-        }
-        __syncthreads();
-    }
-    return nodes[0].val;
-}
+constexpr int kMaxLevels = kPairwiseMaxLevels;
 
 // In-place inclusive scan of buf[0..K): warp w owns the contiguous segment [w*seg, (w+1)*seg) and
 // sweeps it 32 elements at a time (conflict-free smem access, shuffle scan + carry).  The scan is
@@ -294,7 +214,7 @@ __global__ void __launch_bounds__(256) smc_step_kernel(const StepParams p)
                 bufB[k] = is_max ? 0.0f : np_expf(__fsub_rn(v, vmax));
             }
             cnt = block_allreduce(cnt, 0, OpSumI(), s_redi); // contains __syncthreads
-            float s = pairwise_tree_sum(bufB, nodes, s_lvl, s_nlevels);
+            float s = pairwise_tree_sum<false>(bufB, nodes, s_lvl, s_nlevels);
             const float m = (float)cnt;
             if (s != 0.0f) s = __fdiv_rn(s, m);
             lse = __fadd_rn(__fadd_rn(fd_log1pf(s), np_logf(m)), vmax);
@@ -402,6 +322,10 @@ __global__ void __launch_bounds__(256) smc_step_kernel(const StepParams p)
     }
 }
 
+bool smc_step_reg_supported(int64_t K, bool vec);
+int launch_smc_step_reg(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
+                        int32_t *, const float *, float *, int64_t, int32_t *, int, cudaStream_t);
+
 static int g_sm_count = 0;
 static int sm_count()
 {
@@ -447,6 +371,9 @@ int launch_smc_step(const float *a, const float *b, const float *c, const double
                                reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(log_w);
         p.vec = ((K & 3) == 0) && ((bits & 15) == 0);
     }
+    if (stage == 0 && smc_step_reg_supported(K, p.vec != 0) &&
+        ((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(idx)) & 15) == 0)
+        return launch_smc_step_reg(a, b, c, u, B, K, log_w, lse, idx, x_in, x_out, D, flags, mode, stream);
     const size_t smem = step_smem_bytes((int)K, exact);
     if (smem > (size_t)kSmemBudget) {
         set_error("aesmc_smc_step_f32: K=%lld exceeds the single-CTA shared-memory path (max %lld)",
@@ -456,6 +383,7 @@ int launch_smc_step(const float *a, const float *b, const float *c, const double
     const int threads = K >= 2048 ? 256 : (K >= 512 ? 128 : 64);
     auto kern = exact ? smc_step_kernel<true> : smc_step_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
