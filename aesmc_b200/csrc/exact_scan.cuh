@@ -1,0 +1,203 @@
+// exact_scan.cuh -- the reference's SEQUENTIAL float32 cumulative sum, computed in parallel, bit-exactly.
+//
+// np.cumsum over float32 weights (inference.py:257) is the chain s_k = RN(s_{k-1} + w_k).  Rounding
+// makes it non-associative, so a parallel scan in float arithmetic flips ~1e-3 of the ancestor indices
+// at K = 4096 (hard part 1).  The chain is nevertheless parallelisable exactly:
+//
+//   * while s stays inside one binade [2^e, 2^(e+1)) it is an integer multiple m*u of u = 2^(e-23),
+//     and RN(s + w) = (m + q + r)*u with q = floor(w/u) and r the round-to-nearest-even decision,
+//     which depends on s only through the PARITY of m (ties) -- so a block of additions is the map
+//     m -> m + c[m & 1] for two integers (c0, c1), and such maps compose associatively;
+//   * weights are non-negative, so s is monotone and visits each binade once; an approximate prefix
+//     (plain float scan) with a rigorous error bound tells, for each thread's block of 16 particles,
+//     whether the whole block provably lies inside one binade ("pure") or may straddle a boundary
+//     ("mixed", ~10 blocks per row).
+//
+// Pure blocks reduce to (c0, c1) in registers, runs of pure blocks are composed with a segmented
+// shuffle scan, one thread walks the ~20 run/mixed segments (O(1) per run, 16 real float additions per
+// mixed block), and every thread then replays its own block from its exact entry state.  Every block
+// re-verifies that its partial sums stayed inside the assumed binade; if any check fails the caller
+// falls back to the plain sequential chain, so the result is always the reference's bits.
+#pragma once
+#include "common.cuh"
+#include "pairwise.cuh"
+
+namespace aesmc {
+
+constexpr int kScanItems = 16;
+
+struct ExactScanShared {
+    int tail0[32], tail1[32], tailf[32], cnt[32];
+    float wsum[32];
+    int nseg, fail;
+    float total;
+};
+
+__device__ __forceinline__ float sig_to_float(int eb, int m)
+{   // m in [2^23, 2^24]: m * 2^(eb-127-23)
+    return (m >= 0x1000000) ? __int_as_float((eb + 1) << 23) : __int_as_float((eb << 23) | (m & 0x7fffff));
+}
+
+// One addition of the chain in integer form: m <- RN_even(m + y), y = q + f with the tie flag.
+__device__ __forceinline__ int chain_step(int m, int q, int up, int tie)
+{
+    const int t = m + q;
+    return t + (tie ? (t & 1) : up);
+}
+
+// w: in, this thread's 16 weights (blocked layout, zeros beyond K); out, the reference's cumulative
+// sums for the same particles.  bufW4: the weights in the swizzled row buffer (read by the segment
+// walker for mixed blocks; left untouched).  scratch: >= 6*NT ints of shared memory.  Returns true on
+// success with *total = cumulative sum of the whole row; false if a verification failed (w is then
+// unspecified and the caller recomputes the row with the sequential chain).
+__device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
+                                                     int *scratch, ExactScanShared &sh)
+{
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
+    int *recG0 = scratch + NT;           // inclusive composed map of the run up to this block
+    int *recG1 = scratch + 2 * NT;
+    int *seg_end = scratch + 3 * NT;     // last block of every segment, in order
+    float *seg_state = reinterpret_cast<float *>(scratch + 4 * NT); // chain value at each segment start (NT+1)
+
+    // ---- approximate prefix with an error bound ---------------------------------------------------
+    float ls = 0.f;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) ls += w[j];
+    float incl = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) sh.wsum[warp] = incl;
+    __syncthreads();
+    float woff = 0.f;
+    for (int v = 0; v < warp; ++v) woff += sh.wsum[v];
+    const float p_in = woff + (incl - ls), p_out = woff + incl;
+    // |chain - real prefix| <= k * 2^-24 relative (each RN adds <= 2^-24 of the running sum); the
+    // float scan above adds < 64 further roundings.
+    const float eps = (float)(kScanItems * (tid + 1) + 64) * 5.9604644775390625e-08f;
+    const float lo = __fmul_rd(p_in, 1.0f - eps), hi = __fmul_ru(p_out, 1.0f + eps);
+    int eb = 0;
+    if (lo >= 7.8886090522101181e-31f) { // 2^-100: keeps 2^(23-e) representable
+        const int el = __float_as_int(lo) >> 23, eh = __float_as_int(hi) >> 23;
+        if (el == eh) eb = el;
+    }
+
+    // ---- pure block -> (c0, c1) -----------------------------------------------------------------------
+    int c0 = 0, c1 = 0;
+    const float scale = __int_as_float((277 - (eb ? eb : 127)) << 23); // 2^(23 - e)
+    if (eb) {
+        int m0 = 0, m1 = 1;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            const float y = __fmul_rn(w[j], scale); // exact (power of two), < 2^24 for a pure block
+            const int qi = __float2int_rz(y);
+            const float f = __fsub_rn(y, __int2float_rn(qi));
+            const int up = f > 0.5f, tie = f == 0.5f;
+            m0 = chain_step(m0, qi, up, tie);
+            m1 = chain_step(m1, qi, up, tie);
+        }
+        c0 = m0;
+        c1 = m1 - 1;
+    }
+    recE[tid] = eb;
+    __syncthreads();
+
+    // ---- segmented composition of the maps over runs of pure blocks -------------------------------
+    const int eb_prev = tid ? recE[tid - 1] : 0;
+    const int eb_next = (tid + 1 < NT) ? recE[tid + 1] : 0;
+    const bool head = (eb == 0) || (eb_prev != eb);                  // first block of its segment
+    const bool tail = (tid + 1 == NT) || (eb_next == 0) || (eb_next != eb); // last block of its segment
+    int g0 = c0, g1 = c1, hf = head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int p0 = __shfl_up_sync(kFull, g0, o), p1 = __shfl_up_sync(kFull, g1, o);
+        const int pf = __shfl_up_sync(kFull, hf, o);
+        if (lane >= o && !hf) { // (prev then mine): H[p] = P[p] + G[(p + P[p]) & 1]
+            const int n0 = p0 + ((p0 & 1) ? g1 : g0);
+            const int n1 = p1 + (((1 + p1) & 1) ? g1 : g0);
+            g0 = n0; g1 = n1; hf = pf;
+        }
+    }
+    const unsigned endmask = __ballot_sync(kFull, tail);
+    if (lane == 31) { sh.tail0[warp] = g0; sh.tail1[warp] = g1; sh.tailf[warp] = hf; sh.cnt[warp] = __popc(endmask); }
+    __syncthreads();
+    int k0 = 0, k1 = 0, segbase = 0; // carry map of the open segment entering this warp
+    for (int v = 0; v < warp; ++v) {
+        const int t0 = sh.tail0[v], t1 = sh.tail1[v];
+        if (sh.tailf[v]) { k0 = t0; k1 = t1; }
+        else { const int n0 = k0 + ((k0 & 1) ? t1 : t0), n1 = k1 + (((1 + k1) & 1) ? t1 : t0); k0 = n0; k1 = n1; }
+        segbase += sh.cnt[v];
+    }
+    if (!hf) {
+        const int n0 = k0 + ((k0 & 1) ? g1 : g0), n1 = k1 + (((1 + k1) & 1) ? g1 : g0);
+        g0 = n0; g1 = n1;
+    }
+    recG0[tid] = g0;
+    recG1[tid] = g1;
+    const int segidx = segbase + __popc(endmask & ((1u << lane) - 1u));
+    if (tail) seg_end[segidx] = tid;
+    if (tid == NT - 1) sh.nseg = segidx + 1;
+    __syncthreads();
+
+    // ---- one thread walks the segments: O(1) per pure run, 16 float additions per mixed block -----
+    if (tid == 0) {
+        float s = 0.f;
+        int fail = 0;
+        const int nseg = sh.nseg;
+        seg_state[0] = s;
+        for (int i = 0; i < nseg; ++i) {
+            const int t = seg_end[i];
+            const int e = recE[t];
+            if (e) {
+                const int sb = __float_as_int(s);
+                if ((sb >> 23) != e) { fail = 1; break; }
+                int m = (sb & 0x7fffff) | 0x800000;
+                m += (m & 1) ? recG1[t] : recG0[t];
+                if (m > 0x1000000 || m < 0x800000) { fail = 1; break; }
+                s = sig_to_float(e, m);
+            } else {
+#pragma unroll
+                for (int c = 0; c < kScanItems / 4; ++c) {
+                    const float4 v = bufW4[swz(4 * t + c)];
+                    s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+                }
+            }
+            seg_state[i + 1] = s;
+        }
+        sh.total = s;
+        sh.fail = fail;
+    }
+    __syncthreads();
+
+    // ---- every thread replays its own block from its exact entry state ----------------------------
+    int bad = sh.fail;
+    const float s0 = seg_state[segidx];
+    if (eb) {
+        const int sb = __float_as_int(s0);
+        int m = (sb & 0x7fffff) | 0x800000;
+        if ((sb >> 23) != eb) bad = 1;
+        if (!head) m += (m & 1) ? recG1[tid - 1] : recG0[tid - 1];
+        if (m < 0x800000) bad = 1;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            const float y = __fmul_rn(w[j], scale);
+            const int qi = __float2int_rz(y);
+            const float f = __fsub_rn(y, __int2float_rn(qi));
+            m = chain_step(m, qi, f > 0.5f, f == 0.5f);
+            w[j] = sig_to_float(eb, m);
+            // the sum may land exactly on 2^(e+1), but only as the block's last value
+            if (m > 0x1000000 || (m == 0x1000000 && j + 1 < kScanItems)) bad = 1;
+        }
+    } else {
+        float s = s0;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) { s = __fadd_rn(s, w[j]); w[j] = s; }
+    }
+    *total = sh.total;
+    return __syncthreads_or(bad) == 0;
+}
+
+} // namespace aesmc

@@ -222,3 +222,33 @@ def test_full_size_properties(cuda):
     idx_ref, _, lse_ref, _, _ = oracle.sample_ancestral_index(lw_rows, u[rows].cpu().numpy(), return_parts=True)
     assert np.array_equal(idx[rows].cpu().numpy(), idx_ref.astype(np.int32))
     assert np.array_equal(bits(lse[rows].cpu().numpy()), bits(lse_ref))
+
+
+@pytest.mark.parametrize("K", [64, 256, 1000, 4096, 8192, 16384])
+def test_exact_parallel_cumsum_stress(cuda, K):
+    """The parallel evaluation of np.cumsum's sequential float32 chain (exact_scan.cuh) against the
+    oracle on weight profiles that stress binade crossings, ties and absorbed (sub-ulp) weights."""
+    rng = np.random.default_rng(K)
+    rows = []
+    rows.append(rng.standard_normal(K) - 1.4)                                   # typical
+    rows.append(rng.standard_normal(K) * 6)                                     # heavy tailed
+    rows.append(np.sort(rng.standard_normal(K) * 3))                            # increasing: many tiny weights first
+    rows.append(np.sort(rng.standard_normal(K) * 3)[::-1])                      # decreasing: mass first, absorbed tail
+    rows.append(np.full(K, -0.5))                                               # equal weights: ties at every binade
+    rows.append(np.log(2.0) * rng.integers(-30, 0, K))                          # dyadic weights
+    rows.append(np.where(rng.random(K) < 0.9, -np.inf, rng.standard_normal(K))) # mostly zero weights
+    r = rng.standard_normal(K) * 0.01 - 70.0
+    r[K // 3] = 0.0
+    rows.append(r)                                                              # one dominant particle, denormal rest
+    rows.append(np.concatenate([np.full(K // 2, -40.0), rng.standard_normal(K - K // 2)]))  # long sub-ulp prefix
+    rows.append(np.log(np.maximum(rng.integers(0, 4, K), 1e-30) + 0.0))         # small integer weights incl. zeros
+    lw = np.stack(rows).astype(np.float32)
+    lw = np.concatenate([lw, (rng.standard_normal((54, K)) * rng.uniform(0.2, 5, (54, 1))).astype(np.float32)])
+    B = lw.shape[0]
+    u = rng.random(B)
+    (_, lse, idx, _), fl = run_step(lw, u, cuda)
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+    assert fl == 0 and st == 0
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+    bad = np.nonzero((idx.cpu().numpy() != np.minimum(idx_ref, K - 1)).any(axis=1))[0]
+    assert bad.size == 0, "rows with index mismatches: %s" % bad[:10]
