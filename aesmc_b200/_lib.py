@@ -34,6 +34,7 @@ _PROTOTYPES = {
     "aesmc_iota_index_i32": [_i64, _i64, _vp, _vp],
     "aesmc_index_widen": [_vp, _vp, _i64, _vp],
     "aesmc_index_narrow": [_vp, _vp, _i64, _vp],
+    "aesmc_selftest_expf": [_vp, _vp],
     "aesmc_log_ess_f32": [_vp, _i64, _i64, _vp, _vp],
     "aesmc_log_ess_f64": [_vp, _i64, _i64, _vp, _vp],
     "aesmc_weighted_moments_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp],

@@ -48,6 +48,7 @@ int launch_compose_index(const int32_t *, const int32_t *, int64_t, int64_t, int
 int launch_iota_index(int64_t, int64_t, int32_t *, cudaStream_t);
 int launch_index_widen(const int32_t *, int64_t *, int64_t, cudaStream_t);
 int launch_index_narrow(const int64_t *, int32_t *, int64_t, cudaStream_t);
+int launch_selftest_expf(unsigned long long *, cudaStream_t);
 
 } // namespace aesmc
 
@@ -205,6 +206,13 @@ int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream)
     REQUIRE(in && out && n >= 0, fn);
     if (n == 0) return AESMC_OK;
     return launch_index_narrow(in, out, n, S(stream));
+}
+
+int aesmc_selftest_expf(uint64_t *out2, void *stream)
+{
+    const char *fn = "aesmc_selftest_expf";
+    REQUIRE(out2 != nullptr, fn);
+    return launch_selftest_expf(reinterpret_cast<unsigned long long *>(out2), S(stream));
 }
 
 int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream)

@@ -5,19 +5,20 @@
 // at K = 4096 (hard part 1).  The chain is nevertheless parallelisable exactly:
 //
 //   * while s stays inside one binade [2^e, 2^(e+1)) it is an integer multiple m*u of u = 2^(e-23),
-//     and RN(s + w) = (m + q + r)*u with q = floor(w/u) and r the round-to-nearest-even decision,
-//     which depends on s only through the PARITY of m (ties) -- so a block of additions is the map
-//     m -> m + c[m & 1] for two integers (c0, c1), and such maps compose associatively;
+//     and RN(s + w) = RN_even(m + w/u) * u: the rounding depends on s only through the PARITY of m
+//     (ties), so a block of additions is the map m -> m + c[m & 1] for two integers (c0, c1), and such
+//     maps compose associatively.  (c0, c1) are obtained by running the block's additions, scaled by
+//     1/u, from the two representative starts 2^23 and 2^23 + 1: one FADD per particle per parity.
 //   * weights are non-negative, so s is monotone and visits each binade once; an approximate prefix
 //     (plain float scan) with a rigorous error bound tells, for each thread's block of 16 particles,
 //     whether the whole block provably lies inside one binade ("pure") or may straddle a boundary
 //     ("mixed", ~10 blocks per row).
 //
-// Pure blocks reduce to (c0, c1) in registers, runs of pure blocks are composed with a segmented
-// shuffle scan, one thread walks the ~20 run/mixed segments (O(1) per run, 16 real float additions per
-// mixed block), and every thread then replays its own block from its exact entry state.  Every block
-// re-verifies that its partial sums stayed inside the assumed binade; if any check fails the caller
-// falls back to the plain sequential chain, so the result is always the reference's bits.
+// Runs of pure blocks are composed with a segmented shuffle scan, one thread walks the ~20 run/mixed
+// segments (O(1) per run, 16 real float additions per mixed block), and every thread then replays its
+// own block from its exact entry state.  Every block re-verifies that its partial sums stayed inside
+// the assumed binade; if any check fails the caller falls back to the plain sequential chain, so the
+// result is always the reference's bits.
 #pragma once
 #include "common.cuh"
 #include "pairwise.cuh"
@@ -33,27 +34,22 @@ struct ExactScanShared {
     float total;
 };
 
-__device__ __forceinline__ float sig_to_float(int eb, int m)
-{   // m in [2^23, 2^24]: m * 2^(eb-127-23)
-    return (m >= 0x1000000) ? __int_as_float((eb + 1) << 23) : __int_as_float((eb << 23) | (m & 0x7fffff));
-}
-
-// One addition of the chain in integer form: m <- RN_even(m + y), y = q + f with the tie flag.
-__device__ __forceinline__ int chain_step(int m, int q, int up, int tie)
+// (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
+__device__ __forceinline__ void compose_maps(int p0, int p1, int n0, int n1, int &h0, int &h1)
 {
-    const int t = m + q;
-    return t + (tie ? (t & 1) : up);
+    h0 = p0 + ((p0 & 1) ? n1 : n0);
+    h1 = p1 + (((1 + p1) & 1) ? n1 : n0);
 }
 
 // w: in, this thread's 16 weights (blocked layout, zeros beyond K); out, the reference's cumulative
-// sums for the same particles.  bufW4: the weights in the swizzled row buffer (read by the segment
-// walker for mixed blocks; left untouched).  scratch: >= 6*NT ints of shared memory.  Returns true on
-// success with *total = cumulative sum of the whole row; false if a verification failed (w is then
-// unspecified and the caller recomputes the row with the sequential chain).
+// sums for the same particles.  bufW4: the weights in the padded row buffer (read by the segment
+// walker for mixed blocks; left untouched).  scratch: >= 5*NT + 1 ints of shared memory.  Returns
+// true on success with *total = cumulative sum of the whole row; false if a verification failed (w
+// is then unspecified and the caller recomputes the row with the sequential chain).
 __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
                                                      int *scratch, ExactScanShared &sh)
 {
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
     int *recG0 = scratch + NT;           // inclusive composed map of the run up to this block
     int *recG1 = scratch + 2 * NT;
@@ -85,22 +81,23 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         if (el == eh) eb = el;
     }
 
-    // ---- pure block -> (c0, c1) -----------------------------------------------------------------------
+    // ---- pure block -> (c0, c1): the scaled chain from an even and an odd start -------------------
+    const float scale = __int_as_float((277 - (eb ? eb : 127)) << 23); // 2^(23 - e), exact multiplier
     int c0 = 0, c1 = 0;
-    const float scale = __int_as_float((277 - (eb ? eb : 127)) << 23); // 2^(23 - e)
     if (eb) {
-        int m0 = 0, m1 = 1;
+        float m0 = 8388608.0f, m1 = 8388609.0f; // 2^23, 2^23 + 1: ulp 1, so RN == round-half-even to integer
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            const float y = __fmul_rn(w[j], scale); // exact (power of two), < 2^24 for a pure block
-            const int qi = __float2int_rz(y);
-            const float f = __fsub_rn(y, __int2float_rn(qi));
-            const int up = f > 0.5f, tie = f == 0.5f;
-            m0 = chain_step(m0, qi, up, tie);
-            m1 = chain_step(m1, qi, up, tie);
+            const float y = __fmul_rn(w[j], scale);
+            m0 = __fadd_rn(m0, y);
+            m1 = __fadd_rn(m1, y);
         }
-        c0 = m0;
-        c1 = m1 - 1;
+        if (m1 < 16777216.0f) { // still in the ulp-1 regime (always true for a genuinely pure block)
+            c0 = __float_as_int(m0) & 0x7fffff;
+            c1 = (__float_as_int(m1) & 0x7fffff) - 1;
+        } else {
+            eb = 0;
+        }
     }
     recE[tid] = eb;
     __syncthreads();
@@ -108,17 +105,16 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     // ---- segmented composition of the maps over runs of pure blocks -------------------------------
     const int eb_prev = tid ? recE[tid - 1] : 0;
     const int eb_next = (tid + 1 < NT) ? recE[tid + 1] : 0;
-    const bool head = (eb == 0) || (eb_prev != eb);                  // first block of its segment
+    const bool head = (eb == 0) || (eb_prev != eb);                         // first block of its segment
     const bool tail = (tid + 1 == NT) || (eb_next == 0) || (eb_next != eb); // last block of its segment
     int g0 = c0, g1 = c1, hf = head;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int p0 = __shfl_up_sync(kFull, g0, o), p1 = __shfl_up_sync(kFull, g1, o);
         const int pf = __shfl_up_sync(kFull, hf, o);
-        if (lane >= o && !hf) { // (prev then mine): H[p] = P[p] + G[(p + P[p]) & 1]
-            const int n0 = p0 + ((p0 & 1) ? g1 : g0);
-            const int n1 = p1 + (((1 + p1) & 1) ? g1 : g0);
-            g0 = n0; g1 = n1; hf = pf;
+        if (lane >= o && !hf) {
+            compose_maps(p0, p1, g0, g1, g0, g1);
+            hf = pf;
         }
     }
     const unsigned endmask = __ballot_sync(kFull, tail);
@@ -128,13 +124,10 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     for (int v = 0; v < warp; ++v) {
         const int t0 = sh.tail0[v], t1 = sh.tail1[v];
         if (sh.tailf[v]) { k0 = t0; k1 = t1; }
-        else { const int n0 = k0 + ((k0 & 1) ? t1 : t0), n1 = k1 + (((1 + k1) & 1) ? t1 : t0); k0 = n0; k1 = n1; }
+        else compose_maps(k0, k1, t0, t1, k0, k1);
         segbase += sh.cnt[v];
     }
-    if (!hf) {
-        const int n0 = k0 + ((k0 & 1) ? g1 : g0), n1 = k1 + (((1 + k1) & 1) ? g1 : g0);
-        g0 = n0; g1 = n1;
-    }
+    if (!hf) compose_maps(k0, k1, g0, g1, g0, g1);
     recG0[tid] = g0;
     recG1[tid] = g1;
     const int segidx = segbase + __popc(endmask & ((1u << lane) - 1u));
@@ -156,12 +149,12 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
                 if ((sb >> 23) != e) { fail = 1; break; }
                 int m = (sb & 0x7fffff) | 0x800000;
                 m += (m & 1) ? recG1[t] : recG0[t];
-                if (m > 0x1000000 || m < 0x800000) { fail = 1; break; }
-                s = sig_to_float(e, m);
+                if (m > 0x1000000) { fail = 1; break; }
+                s = (m == 0x1000000) ? __int_as_float((e + 1) << 23) : __int_as_float((e << 23) | (m & 0x7fffff));
             } else {
 #pragma unroll
                 for (int c = 0; c < kScanItems / 4; ++c) {
-                    const float4 v = bufW4[swz(4 * t + c)];
+                    const float4 v = bufW4[pad_chunk(4 * t + c)];
                     s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
                 }
             }
@@ -180,17 +173,19 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         int m = (sb & 0x7fffff) | 0x800000;
         if ((sb >> 23) != eb) bad = 1;
         if (!head) m += (m & 1) ? recG1[tid - 1] : recG0[tid - 1];
-        if (m < 0x800000) bad = 1;
+        if (m >= 0x1000000) { bad = 1; m = 0x800000; }
+        float mf = __int_as_float(0x4B000000 | (m & 0x7fffff)); // m as a float in [2^23, 2^24)
+        const int unscale = (150 - eb) << 23;                   // multiply by u = 2^(e-23) on the bit pattern
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            const float y = __fmul_rn(w[j], scale);
-            const int qi = __float2int_rz(y);
-            const float f = __fsub_rn(y, __int2float_rn(qi));
-            m = chain_step(m, qi, f > 0.5f, f == 0.5f);
-            w[j] = sig_to_float(eb, m);
-            // the sum may land exactly on 2^(e+1), but only as the block's last value
-            if (m > 0x1000000 || (m == 0x1000000 && j + 1 < kScanItems)) bad = 1;
+            mf = __fadd_rn(mf, __fmul_rn(w[j], scale));
+            w[j] = __int_as_float(__float_as_int(mf) - unscale);
         }
+        // The scaled chain IS the reference chain (power-of-two scaling commutes with rounding), so
+        // these 16 values are exact whatever happens; but the (c0, c1) maps handed to the walker and
+        // to later blocks of this run assumed the ulp-1 regime: landing exactly on 2^(e+1) is still
+        // consistent (a following block of the same run rejects m_in = 2^24 above), going past is not.
+        if (mf > 16777216.0f) bad = 1;
     } else {
         float s = s0;
 #pragma unroll

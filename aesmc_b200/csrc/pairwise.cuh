@@ -19,9 +19,11 @@ constexpr int kPairwiseMaxLevels = 40;
 
 __host__ __device__ inline int pairwise_max_nodes(int K) { return 2 * (K / 56 + 2); }
 
-// XOR swizzle of float4 chunks used by the register-blocked kernel's row buffer
-__device__ __forceinline__ int swz(int c) { return c ^ ((c >> 3) & 7); }
-__device__ __forceinline__ int elem_addr(int k) { return (swz(k >> 2) << 2) | (k & 3); }
+// Padded row layout of the register-blocked kernel: one spare 16-byte chunk after every 8 chunks
+// (4 floats per 32).  Striped float4 accesses (chunk = t + NT*i) and blocked ones (chunk = 4t + i)
+// are both bank-conflict free, and addresses stay affine for unrolled loops.
+__device__ __forceinline__ int pad_chunk(int c) { return c + (c >> 3); }
+__device__ __forceinline__ int pad_elem(int k) { return k + ((k >> 5) << 2); }
 
 static __device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *nlevels, int K)
 {
@@ -49,15 +51,15 @@ static __device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *n
     *nlevels = L;
 }
 
-// Sum of the K floats of a row in numpy's pairwise order.  SWZ: the row is stored with the chunk
-// swizzle above.  All threads of the CTA call; the result is returned to all.
-template <bool SWZ>
+// Sum of the K floats of a row in numpy's pairwise order.  PAD: the row is stored in the padded
+// layout above.  All threads of the CTA call; the result is returned to all.
+template <bool PAD>
 static __device__ float pairwise_tree_sum(const float *buf, PwNode *nodes, const int *lvl_start, int nlevels)
 {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int nnodes = lvl_start[nlevels];
     const int grp = tid >> 3, j = tid & 7, ngrp = NT >> 3;
-    auto at = [&](int k) { return buf[SWZ ? elem_addr(k) : k]; };
+    auto at = [&](int k) { return buf[PAD ? pad_elem(k) : k]; };
     for (int base = 0; base < nnodes; base += ngrp) { // warp-uniform trip count
         const int n = base + grp;
         const bool valid = (n < nnodes) && (nodes[n].child < 0);

@@ -201,6 +201,30 @@ __global__ void weighted_moments_kernel(const float *__restrict__ x, const float
     }
 }
 
+// Exhaustive device-side check of np_expf_nonpos against np_expf over every float in [-104, -0] and
+// -inf: out[0] = number of bit mismatches, out[1] = bit pattern of one mismatching input.
+__global__ void selftest_expf_kernel(unsigned long long *out)
+{
+    const unsigned long long n = 0x42D00000ull + 1ull; // patterns 0x80000000 .. 0xC2D00000, then -inf
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0, where = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const unsigned bits = (i == n) ? 0xFF800000u : (0x80000000u + (unsigned)i);
+        const float x = __uint_as_float(bits);
+        if (__float_as_uint(np_expf_nonpos(x)) != __float_as_uint(np_expf(x))) { ++bad; where = bits; }
+    }
+    if (bad) { atomicAdd(out, bad); atomicExch(out + 1, where); }
+}
+
+int launch_selftest_expf(unsigned long long *out, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, 16, st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
+    selftest_expf_kernel<<<148 * 16, 256, 0, st>>>(out);
+    count_launch();
+    return check_launch("selftest_expf_kernel");
+}
+
 static int row_threads(int64_t K) { return K >= 4096 ? 256 : (K >= 1024 ? 128 : (K >= 128 ? 64 : 32)); }
 static unsigned row_grid(int64_t B, int threads)
 {

@@ -124,6 +124,11 @@ int aesmc_iota_index_i32(int64_t B, int64_t K, int32_t *out, void *stream);
 int aesmc_index_widen(const int32_t *in, int64_t *out, int64_t n, void *stream);
 int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream);
 
+/* Device self-test: compares the hot path's specialised float32 exp (non-positive arguments, custom
+ * correctly-rounded division) with the general reference-order exp for EVERY float in [-104, -0] and
+ * -inf.  out2: device uint64[2] = {number of mismatching inputs, bit pattern of one of them}. */
+int aesmc_selftest_expf(uint64_t *out2, void *stream);
+
 /* statistics.log_ess (statistics.py:79-91): 2*lse(lw) - lse(2*lw) per row. */
 int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream);
 int aesmc_log_ess_f64(const double *log_w, int64_t B, int64_t K, double *out, void *stream);

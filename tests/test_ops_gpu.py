@@ -197,3 +197,15 @@ def test_index_utils(cuda):
     i = torch.randint(0, 1000, (5, 77), device=cuda)
     assert torch.equal(_ops.widen_index(_ops.narrow_index(i)), i)
     assert torch.equal(_ops.iota_index(3, 9, cuda).long(), torch.arange(9, device=cuda).expand(3, 9))
+
+
+def test_specialised_expf_exhaustive(cuda):
+    """np_expf_nonpos (hot-path exp: custom correctly-rounded division, no range tests) equals the
+    general reference-order np_expf for EVERY float in [-104, -0] and -inf (1.12e9 inputs, on device);
+    np_expf itself is pinned to numpy's bits through the oracle in test_step_parity_gpu.py."""
+    from aesmc_b200 import _lib
+    out = torch.zeros(2, dtype=torch.int64, device=cuda)
+    _lib.call("aesmc_selftest_expf", out.data_ptr())
+    torch.cuda.synchronize()
+    mism, where = (int(v) for v in out.cpu())
+    assert mism == 0, "np_expf_nonpos differs from np_expf on %d inputs, e.g. bits 0x%08x" % (mism, where)
