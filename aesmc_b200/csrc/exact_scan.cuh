@@ -43,7 +43,8 @@ __device__ __forceinline__ void compose_maps(int p0, int p1, int n0, int n1, int
 
 // w: in, this thread's 16 weights (blocked layout, zeros beyond K); out, the reference's cumulative
 // sums for the same particles.  bufW4: the weights in the padded row buffer (read by the segment
-// walker for mixed blocks; left untouched).  scratch: >= 5*NT + 1 ints of shared memory.  Returns
+// walker for mixed blocks; left untouched).  scratch: >= 8*NT + 4 ints of shared memory, 16-byte
+// aligned.  Returns
 // true on success with *total = cumulative sum of the whole row; false if a verification failed (w
 // is then unspecified and the caller recomputes the row with the sequential chain).
 __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
@@ -53,8 +54,8 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
     int *recG0 = scratch + NT;           // inclusive composed map of the run up to this block
     int *recG1 = scratch + 2 * NT;
-    int *seg_end = scratch + 3 * NT;     // last block of every segment, in order
-    float *seg_state = reinterpret_cast<float *>(scratch + 4 * NT); // chain value at each segment start (NT+1)
+    float *seg_state = reinterpret_cast<float *>(scratch + 3 * NT); // chain value at each segment start (NT+1)
+    int4 *seg_rec = reinterpret_cast<int4 *>(scratch + 4 * NT + 4);  // per segment: (last block, binade, c0, c1)
 
     // ---- approximate prefix with an error bound ---------------------------------------------------
     float ls = 0.f;
@@ -131,7 +132,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     recG0[tid] = g0;
     recG1[tid] = g1;
     const int segidx = segbase + __popc(endmask & ((1u << lane) - 1u));
-    if (tail) seg_end[segidx] = tid;
+    if (tail) seg_rec[segidx] = make_int4(tid, eb, g0, g1); // everything the walker needs, one load
     if (tid == NT - 1) sh.nseg = segidx + 1;
     __syncthreads();
 
@@ -141,14 +142,15 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         int fail = 0;
         const int nseg = sh.nseg;
         seg_state[0] = s;
+        int4 rec = seg_rec[0];
         for (int i = 0; i < nseg; ++i) {
-            const int t = seg_end[i];
-            const int e = recE[t];
+            const int t = rec.x, e = rec.y, r0 = rec.z, r1 = rec.w;
+            if (i + 1 < nseg) rec = seg_rec[i + 1]; // independent of the chain: overlaps with it
             if (e) {
                 const int sb = __float_as_int(s);
                 if ((sb >> 23) != e) { fail = 1; break; }
                 int m = (sb & 0x7fffff) | 0x800000;
-                m += (m & 1) ? recG1[t] : recG0[t];
+                m += (m & 1) ? r1 : r0;
                 if (m > 0x1000000) { fail = 1; break; }
                 s = (m == 0x1000000) ? __int_as_float((e + 1) << 23) : __int_as_float((e << 23) | (m & 0x7fffff));
             } else {

@@ -98,7 +98,11 @@ def log_prob(distribution, value):
     lead = value.dim() - len(distribution.event_shape)  # number of batch-like dims of value
     have = len(distribution.batch_shape)
     if lead == have or lead == have + 2:
-        distribution._validate_sample(value)
+        # The reference validates the sample unconditionally (state.py:142), which costs a host
+        # synchronisation per call on CUDA tensors; here a distribution built with
+        # validate_args=False (or under Distribution.set_default_validate_args(False)) is trusted.
+        if getattr(distribution, "_validate_args", True):
+            distribution._validate_sample(value)
         lp = distribution.log_prob(value)
     elif lead == have + 1:  # batch-expanded distribution: particles must lead for broadcasting
         lp = distribution.log_prob(value.transpose(0, 1)).transpose(0, 1)

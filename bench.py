@@ -204,6 +204,9 @@ def run_native(args):
         u_host = torch.from_numpy(np.random.default_rng(7 + rank).random((T - 1, B))).pin_memory()
         out_host = torch.empty(B, dtype=torch.float32).pin_memory()
         models = lgssm.bootstrap_filter(device=dev)
+        # production setting for torch.distributions: argument/sample validation reads a device flag on
+        # the host for every distribution built and every log_prob (7 synchronisations per time step)
+        torch.distributions.Distribution.set_default_validate_args(False)
         del log_w, idx
         torch.cuda.empty_cache()
 
@@ -233,7 +236,8 @@ def run_native(args):
         e2e = {"value": world * B * K * T / (e_seconds / reps), "unit": UNIT,
                "h2d_bytes_per_step": obs_host.numel() * 4 + u_host.numel() * 8, "d2h_bytes_per_step": B * 4,
                "ms_per_step": e_seconds * 1e3 / reps, "steps": reps,
-               "api": "aesmc_b200.inference.infer('smc', bootstrap LGSSM user model in torch eager)"}
+               "api": "aesmc_b200.inference.infer('smc', bootstrap LGSSM user model in torch eager, "
+                      "Distribution.set_default_validate_args(False))"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample ---------
     cpu_baseline = None
