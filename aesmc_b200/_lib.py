@@ -20,6 +20,8 @@ _vp, _i64, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
 # name -> argtypes; every function returns int unless listed in _RESTYPES
 _PROTOTYPES = {
     "aesmc_smc_step_f32": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _int, _vp],
+    "aesmc_smc_step_ws_f32": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _int, _vp, _i64, _vp],
+    "aesmc_smc_step_workspace_bytes": [_i64, _i64],
     "aesmc_resample_from_weights_f32": [_vp, _vp, _i64, _i64, _vp, _vp, _int, _vp],
     "aesmc_resample_from_cdf_f32": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "aesmc_is_accumulate_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
@@ -47,6 +49,7 @@ _RESTYPES = {
     "aesmc_last_error_string": ctypes.c_char_p,
     "aesmc_launch_count": _i64,
     "aesmc_max_particles_single_cta": _i64,
+    "aesmc_smc_step_workspace_bytes": _i64,
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -80,9 +80,11 @@ class _SMCStep(torch.autograd.Function):
         if resample and x is not None:
             D = x[0, 0].numel()
             x_out = torch.empty_like(x)
-        _lib.call("aesmc_smc_step_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(u), B, K,
+        ws_bytes = int(_lib.load().aesmc_smc_step_workspace_bytes(B, K))  # > 0: multi-CTA path (large K)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
+        _lib.call("aesmc_smc_step_ws_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(u), B, K,
                   _lib.ptr(log_w), _lib.ptr(lse), _lib.ptr(idx), _lib.ptr(x if x_out is not None else None),
-                  _lib.ptr(x_out), D, _lib.ptr(flags), mode)
+                  _lib.ptr(x_out), D, _lib.ptr(flags), mode, _lib.ptr(ws), ws_bytes)
         ctx.save_for_backward(log_w, lse, idx)
         ctx.has = (b is not None, c is not None, x_out is not None)
         ctx.x_shape = None if x is None else x.shape

@@ -31,7 +31,8 @@ int check_launch(const char *what)
 // kernels (smc_step.cu, reduce.cu, gather.cu)
 int64_t max_particles_single_cta();
 int launch_smc_step(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
-                    int32_t *, const float *, float *, int64_t, int32_t *, int, int, cudaStream_t);
+                    int32_t *, const float *, float *, int64_t, int32_t *, int, int, void *, int64_t, cudaStream_t);
+int64_t step_workspace_bytes(int64_t B, int64_t K);
 int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
 int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
 int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
@@ -72,9 +73,23 @@ const char *aesmc_last_error_string(void) { return g_err; }
 int64_t aesmc_launch_count(void) { return (int64_t)g_launches.load(); }
 int64_t aesmc_max_particles_single_cta(void) { return max_particles_single_cta(); }
 
+int64_t aesmc_smc_step_workspace_bytes(int64_t B, int64_t K)
+{
+    if (B <= 0 || K <= 0) return 0;
+    return step_workspace_bytes(B, K);
+}
+
 int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u, int64_t B,
                        int64_t K, float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out,
                        int64_t D, int32_t *flags, int mode, void *stream)
+{
+    return aesmc_smc_step_ws_f32(lp_a, lp_b, lp_c, u, B, K, log_w, lse, idx, x_in, x_out, D, flags, mode, nullptr, 0,
+                                 stream);
+}
+
+int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u, int64_t B,
+                          int64_t K, float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out,
+                          int64_t D, int32_t *flags, int mode, void *workspace, int64_t workspace_bytes, void *stream)
 {
     const char *fn = "aesmc_smc_step_f32";
     REQUIRE(lp_a && log_w && flags, fn);
@@ -85,7 +100,8 @@ int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, 
     REQUIRE(x_in == nullptr || (idx != nullptr && D >= 1 && K * D <= kMaxDim), fn);
     REQUIRE(log_w != lp_a && log_w != lp_b && log_w != lp_c, fn);
     if (B == 0) return AESMC_OK;
-    return launch_smc_step(lp_a, lp_b, lp_c, u, B, K, log_w, lse, idx, x_in, x_out, x_in ? D : 1, flags, mode, 0, S(stream));
+    return launch_smc_step(lp_a, lp_b, lp_c, u, B, K, log_w, lse, idx, x_in, x_out, x_in ? D : 1, flags, mode, 0, workspace,
+                           workspace_bytes, S(stream));
 }
 
 int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,
@@ -96,7 +112,8 @@ int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, 
     REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
     REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
     if (B == 0) return AESMC_OK;
-    return launch_smc_step(w, nullptr, nullptr, u, B, K, nullptr, nullptr, idx, nullptr, nullptr, 1, flags, mode, 1, S(stream));
+    return launch_smc_step(w, nullptr, nullptr, u, B, K, nullptr, nullptr, idx, nullptr, nullptr, 1, flags, mode, 1, nullptr, 0,
+                           S(stream));
 }
 
 int aesmc_resample_from_cdf_f32(const float *cdf, const double *u, int64_t B, int64_t K, int32_t *idx,
@@ -107,7 +124,7 @@ int aesmc_resample_from_cdf_f32(const float *cdf, const double *u, int64_t B, in
     REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
     if (B == 0) return AESMC_OK;
     return launch_smc_step(cdf, nullptr, nullptr, u, B, K, nullptr, nullptr, idx, nullptr, nullptr, 1, flags,
-                           AESMC_MODE_EXACT, 2, S(stream));
+                           AESMC_MODE_EXACT, 2, nullptr, 0, S(stream));
 }
 
 int aesmc_is_accumulate_f32(const float *lp_a, const float *lp_b, const float *lp_c, float *acc, float *log_w,

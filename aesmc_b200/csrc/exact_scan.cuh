@@ -48,7 +48,7 @@ __device__ __forceinline__ void compose_maps(int p0, int p1, int n0, int n1, int
 // true on success with *total = cumulative sum of the whole row; false if a verification failed (w
 // is then unspecified and the caller recomputes the row with the sequential chain).
 __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
-                                                     int *scratch, ExactScanShared &sh)
+                                                     int *scratch, ExactScanShared &sh, float s_in = 0.f)
 {
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
@@ -71,7 +71,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     __syncthreads();
     float woff = 0.f;
     for (int v = 0; v < warp; ++v) woff += sh.wsum[v];
-    const float p_in = woff + (incl - ls), p_out = woff + incl;
+    const float p_in = s_in + (woff + (incl - ls)), p_out = s_in + (woff + incl);
     // |chain - real prefix| <= k * 2^-24 relative (each RN adds <= 2^-24 of the running sum); the
     // float scan above adds < 64 further roundings.
     const float eps = (float)(kScanItems * (tid + 1) + 64) * 5.9604644775390625e-08f;
@@ -138,7 +138,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
 
     // ---- one thread walks the segments: O(1) per pure run, 16 float additions per mixed block -----
     if (tid == 0) {
-        float s = 0.f;
+        float s = s_in;
         int fail = 0;
         const int nseg = sh.nseg;
         seg_state[0] = s;

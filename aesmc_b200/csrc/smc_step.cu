@@ -16,6 +16,7 @@
 //   P5  coalesced store of idx, fused ancestral gather of the latent
 #include "common.cuh"
 #include "pairwise.cuh"
+#include "scan.cuh"
 
 namespace aesmc {
 
@@ -37,31 +38,6 @@ struct StepParams {
 };
 
 constexpr int kMaxLevels = kPairwiseMaxLevels;
-
-// In-place inclusive scan of buf[0..K): warp w owns the contiguous segment [w*seg, (w+1)*seg) and
-// sweeps it 32 elements at a time (conflict-free smem access, shuffle scan + carry).  The scan is
-// local to each warp's segment; warp_tot[w] receives the segment total and the caller folds the
-// totals of preceding warps in when it consumes the values.
-template <typename T, typename Op>
-__device__ __forceinline__ void segment_scan_inplace(T *buf, int K, int seg, T identity, Op op, T *warp_tot)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int begin = min(warp * seg, K), end = min(begin + seg, K);
-    T carry = identity;
-    for (int base = begin; base < end; base += 32) {
-        const int k = base + lane;
-        T v = (k < end) ? buf[k] : identity;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            T n = __shfl_up_sync(kFull, v, o);
-            if (lane >= o) v = op(n, v);
-        }
-        v = op(carry, v);
-        if (k < end) buf[k] = v;
-        carry = __shfl_sync(kFull, v, 31);
-    }
-    if (lane == 0) warp_tot[warp] = carry;
-}
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256) smc_step_kernel(const StepParams p)
@@ -322,6 +298,9 @@ __global__ void __launch_bounds__(256) smc_step_kernel(const StepParams p)
     }
 }
 
+int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K);
+int launch_smc_step_large(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
+                          int32_t *, const float *, float *, int64_t, int32_t *, int, void *, int64_t, cudaStream_t);
 bool smc_step_reg_supported(int64_t K, bool vec);
 int launch_smc_step_reg(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
                         int32_t *, const float *, float *, int64_t, int32_t *, int, cudaStream_t);
@@ -348,6 +327,12 @@ static size_t step_smem_bytes(int K, bool exact)
     return bytes;
 }
 
+int64_t step_workspace_bytes(int64_t B, int64_t K)
+{
+    if (step_smem_bytes((int)(K < 2147483647LL ? K : 2147483647LL), true) <= (size_t)kSmemBudget) return 0;
+    return smc_step_large_workspace_bytes(B, K);
+}
+
 int64_t max_particles_single_cta()
 {
     int64_t K = 1024;
@@ -357,7 +342,7 @@ int64_t max_particles_single_cta()
 
 int launch_smc_step(const float *a, const float *b, const float *c, const double *u, int64_t B, int64_t K,
                     float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out, int64_t D,
-                    int32_t *flags, int mode, int stage, cudaStream_t stream)
+                    int32_t *flags, int mode, int stage, void *workspace, int64_t workspace_bytes, cudaStream_t stream)
 {
     const bool exact = (mode == AESMC_MODE_EXACT);
     StepParams p;
@@ -375,6 +360,9 @@ int launch_smc_step(const float *a, const float *b, const float *c, const double
         ((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(idx)) & 15) == 0)
         return launch_smc_step_reg(a, b, c, u, B, K, log_w, lse, idx, x_in, x_out, D, flags, mode, stream);
     const size_t smem = step_smem_bytes((int)K, exact);
+    if (smem > (size_t)kSmemBudget && stage == 0)
+        return launch_smc_step_large(a, b, c, u, B, K, log_w, lse, idx, x_in, x_out, D, flags, mode, workspace,
+                                     workspace_bytes, stream);
     if (smem > (size_t)kSmemBudget) {
         set_error("aesmc_smc_step_f32: K=%lld exceeds the single-CTA shared-memory path (max %lld)",
                   (long long)K, (long long)max_particles_single_cta());

@@ -72,6 +72,17 @@ int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, 
                        void *stream);
 
 /*
+ * Rows too large for one CTA (K > aesmc_max_particles_single_cta()) run a multi-CTA pipeline that needs
+ * caller-allocated device scratch: aesmc_smc_step_workspace_bytes(B, K) bytes (0 when not needed), 256-byte
+ * aligned, passed to aesmc_smc_step_ws_f32 (identical to aesmc_smc_step_f32 otherwise).
+ */
+int64_t aesmc_smc_step_workspace_bytes(int64_t B, int64_t K);
+int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u,
+                          int64_t B, int64_t K, float *log_w, float *lse, int32_t *idx,
+                          const float *x_in, float *x_out, int64_t D, int32_t *flags, int mode,
+                          void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
  * Resampling entered at a later stage (used by the staged parity tests, and useful on their own):
  *   from normalised weights w [B,K]: cumulative sum (inference.py:257), renormalisation by the last
  *   entry (:260-261), search (:263-264);  from a normalised CDF [B,K]: the search alone.
