@@ -19,6 +19,7 @@ from . import inference  # noqa: E402
 from . import statistics  # noqa: E402
 from . import train  # noqa: E402
 from . import distributed  # noqa: E402
+from . import fused  # noqa: E402
 from ._ops import get_resampling_mode, set_resampling_mode  # noqa: E402,F401
 
 

@@ -33,6 +33,10 @@ int64_t max_particles_single_cta();
 int launch_smc_step(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
                     int32_t *, const float *, float *, int64_t, int32_t *, int, int, void *, int64_t, cudaStream_t);
 int64_t step_workspace_bytes(int64_t B, int64_t K);
+bool smc_step_lg_supported(int64_t K);
+int launch_smc_step_lg(const float *, const float *, const float *, const float *, const float *, float,
+                       unsigned long long, unsigned long long, int64_t, int64_t, const double *, float *, float *,
+                       float *, int32_t *, float *, int32_t *, int, cudaStream_t);
 int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
 int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
 int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
@@ -102,6 +106,30 @@ int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_
     if (B == 0) return AESMC_OK;
     return launch_smc_step(lp_a, lp_b, lp_c, u, B, K, log_w, lse, idx, x_in, x_out, x_in ? D : 1, flags, mode, 0, workspace,
                            workspace_bytes, S(stream));
+}
+
+int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
+                          const float *params_host, float half_log_2pi, uint64_t seed, uint64_t stream_offset,
+                          int64_t B, int64_t K, const double *u, float *x_new, float *log_w, float *lse, int32_t *idx,
+                          float *x_out, int32_t *flags, int mode, void *stream)
+{
+    const char *fn = "aesmc_smc_step_lg_f32";
+    REQUIRE(y && params_host && flags, fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
+    REQUIRE((idx == nullptr) == (x_out == nullptr), fn);
+    REQUIRE(idx == nullptr || u != nullptr, fn);
+    if (!smc_step_lg_supported(K)) {
+        set_error("%s: K=%lld not supported by the fused model kernel (64 <= K <= 16384, K %% 4 == 0)", fn, (long long)K);
+        return AESMC_ERR_UNSUPPORTED;
+    }
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(x_prev) | reinterpret_cast<uintptr_t>(noise) |
+                           reinterpret_cast<uintptr_t>(x_new) | reinterpret_cast<uintptr_t>(log_w) |
+                           reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(x_out);
+    REQUIRE((bits & 15) == 0, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_smc_step_lg(x_prev, y, noise, q_off, params_host, half_log_2pi, seed, stream_offset, B, K, u, x_new,
+                              log_w, lse, idx, x_out, flags, mode, S(stream));
 }
 
 int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,

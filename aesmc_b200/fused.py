@@ -1,0 +1,187 @@
+"""Fused-model fast path: scalar linear-Gaussian state-space models whose sampling and
+log-densities are evaluated INSIDE the step kernel (aesmc_smc_step_lg_f32) instead of through ~25 torch
+elementwise kernels per time step.
+
+    x_0 ~ N(m0, s0^2)      x_t | x_{t-1} ~ N(a x_{t-1} + b, sx^2)      y_t | x_t ~ N(c x_t + d, sy^2)
+    proposal: 'bootstrap' (the prior dynamics) or affine-Gaussian
+              q(x_0 | y_0) = N(p0_y y_0 + p0_off, p0_scale^2),  q(x_t | x_{t-1}, y_t) = N(pt_x x_{t-1} + pt_y y_t + pt_off, pt_scale^2)
+
+``ScalarLinearGaussianSSM`` is an ordinary user model: ``.initial / .transition / .emission / .proposal``
+are callables with the reference's conventions returning torch.distributions, so the same object runs
+through the generic path, through the oracle port and through the reference itself.  ``inference.infer``
+recognises the four bound methods of one instance and -- when no gradient is required -- dispatches to
+``infer_fused``: same arguments, same result dict.  The kernel reproduces torch.distributions.Normal's
+float32 arithmetic operation for operation, so with injected noise the fused and the eager path agree
+bit for bit (tests/test_fused_gpu.py); without, noise comes from an in-kernel Philox4x32-10 stream
+seeded from torch's global generator.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, _ops, state
+
+Normal = torch.distributions.Normal
+_FULL = state.BatchShapeMode.FULLY_EXPANDED
+_BATCH = state.BatchShapeMode.BATCH_EXPANDED
+
+
+class ScalarLinearGaussianSSM:
+    def __init__(self, initial_loc=0.0, initial_scale=1.0, transition_mult=0.9, transition_offset=0.0,
+                 transition_scale=1.0, emission_mult=1.0, emission_offset=0.0, emission_scale=0.5,
+                 proposal="bootstrap", device=None):
+        f = lambda v: torch.tensor(float(v), dtype=torch.float32, device=device)  # noqa: E731
+        self.device = device
+        self.m0, self.s0 = f(initial_loc), f(initial_scale)
+        self.a, self.b, self.sx = f(transition_mult), f(transition_offset), f(transition_scale)
+        self.c, self.d, self.sy = f(emission_mult), f(emission_offset), f(emission_scale)
+        if proposal == "bootstrap":
+            self.prop = None
+        else:
+            self.prop = {k: f(proposal[k]) for k in ("p0_y", "p0_off", "p0_scale", "pt_x", "pt_y", "pt_off", "pt_scale")}
+
+    # ---- the reference's callable conventions (eager torch path) ---------------------------------
+    def initial(self):
+        return Normal(self.m0, self.s0)
+
+    def transition(self, previous_latents=None, time=None, previous_observations=None):
+        return state.set_batch_shape_mode(Normal(previous_latents[-1] * self.a + self.b, self.sx), _FULL)
+
+    def emission(self, latents=None, time=None, previous_observations=None):
+        return state.set_batch_shape_mode(Normal(latents[-1] * self.c + self.d, self.sy), _FULL)
+
+    def proposal(self, previous_latents=None, time=None, observations=None):
+        if self.prop is None:
+            return self.initial() if time == 0 else self.transition(previous_latents=previous_latents, time=time)
+        if time == 0:
+            loc = observations[0] * self.prop["p0_y"] + self.prop["p0_off"]
+            return state.set_batch_shape_mode(Normal(loc, self.prop["p0_scale"]), _BATCH)
+        row = observations[time] * self.prop["pt_y"] + self.prop["pt_off"]
+        loc = previous_latents[-1] * self.prop["pt_x"] + row.unsqueeze(1)
+        return state.set_batch_shape_mode(Normal(loc, self.prop["pt_scale"]), _FULL)
+
+    def callables(self):
+        return self.initial, self.transition, self.emission, self.proposal
+
+    # ---- parameters for the fused kernel -------------------------------------------------------------
+    def _affine(self, mult, off, scale):
+        # (mult, off, scale, 2*var, log scale) computed with torch on the model's device, exactly as
+        # Normal.log_prob computes them (float32)
+        return torch.stack([mult, off, scale, 2 * (scale ** 2), scale.log()])
+
+    def kernel_params(self):
+        """float32 [2, 15] on the host: row 0 for t = 0, row 1 for t >= 1; each row = t | e | q."""
+        zero = torch.zeros_like(self.m0)
+        init = self._affine(zero, self.m0, self.s0)
+        trans = self._affine(self.a, self.b, self.sx)
+        emis = self._affine(self.c, self.d, self.sy)
+        if self.prop is None:
+            q0, qt = init, trans
+        else:
+            q0 = self._affine(zero, self.prop["p0_off"], self.prop["p0_scale"])
+            qt = self._affine(self.prop["pt_x"], self.prop["pt_off"], self.prop["pt_scale"])
+        return torch.stack([torch.cat([init, emis, q0]), torch.cat([trans, emis, qt])]).cpu().numpy().astype(np.float32)
+
+    def proposal_row_offset(self, observation, time):
+        """[B] per-row offset of the proposal mean (None when it does not depend on the observation)."""
+        if self.prop is None:
+            return None
+        if time == 0:
+            return (observation * self.prop["p0_y"] + self.prop["p0_off"]).contiguous()
+        return (observation * self.prop["pt_y"] + self.prop["pt_off"]).contiguous()
+
+
+def model_of(initial, transition, emission, proposal):
+    """The ScalarLinearGaussianSSM whose bound methods these four callables are, else None."""
+    owner = getattr(proposal, "__self__", None)
+    if not isinstance(owner, ScalarLinearGaussianSSM):
+        return None
+    for fn, name in ((initial, "initial"), (transition, "transition"), (emission, "emission"), (proposal, "proposal")):
+        if getattr(fn, "__self__", None) is not owner or getattr(fn, "__name__", None) != name:
+            return None
+    return owner
+
+
+def applicable(model, observations, num_particles):
+    if model is None or not torch.cuda.is_available():
+        return False
+    first = observations[0]
+    if isinstance(first, dict) or not torch.is_tensor(first) or first.dim() != 1 or not first.is_cuda:
+        return False
+    if first.dtype != torch.float32 or model.m0.device != first.device:
+        return False
+    return 64 <= num_particles <= 16384 and num_particles % 4 == 0
+
+
+_HALF_LOG_2PI = float(np.float32(math.log(math.sqrt(2 * math.pi))))
+
+
+def infer_fused(model, observations, num_particles, return_log_marginal_likelihood=False, return_latents=True,
+                return_original_latents=False, return_log_weight=True, return_log_weights=False,
+                return_ancestral_indices=False, uniforms=None, resampling_mode=None, check_finite=True, noise=None):
+    """SMC ('smc' only) with the model fused into the step kernel; arguments and result as inference.infer.
+    noise: optional [T, B, K] float32 standard normals to use instead of the in-kernel Philox stream."""
+    from . import inference  # late import: inference imports this module
+    T = len(observations)
+    B = observations[0].size(0)
+    K = num_particles
+    dev = observations[0].device
+    params = model.kernel_params()
+    mode = _ops.mode_code(resampling_mode)
+    flags = _ops.new_flags(dev)
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())  # torch.manual_seed controls the stream
+    keep_originals = return_original_latents or return_latents
+    keep_index = return_ancestral_indices or return_latents
+    originals, log_weights, ancestors = [], [], []
+    lses = torch.empty(T, B, dtype=torch.float32, device=dev)
+    scratch_idx = None if keep_index else torch.empty(B, K, dtype=torch.int32, device=dev)
+    arena = [torch.empty(B, K, dtype=torch.float32, device=dev) for _ in range(2)]
+    x_prev = None
+    x_last = None
+    log_w = None
+    for t in range(T):
+        last = t == T - 1
+        y = observations[t].contiguous()
+        q_off = model.proposal_row_offset(y, t)
+        x_new = torch.empty(B, K, dtype=torch.float32, device=dev) if (keep_originals or last) else None
+        want_lw = return_log_weights or (last and return_log_weight)
+        log_w = torch.empty(B, K, dtype=torch.float32, device=dev) if want_lw else None
+        if last:
+            u_dev = idx = x_out = None
+        else:
+            ut = np.random.uniform(size=[B, 1]) if uniforms is None else uniforms[t]  # inference.py:250
+            u_dev = _ops.uniforms_to_device(ut, B, dev)
+            idx = torch.empty(B, K, dtype=torch.int32, device=dev) if keep_index else scratch_idx
+            x_out = arena[t & 1]
+        nz = None if noise is None else noise[t].contiguous()
+        _lib.call("aesmc_smc_step_lg_f32", _lib.ptr(x_prev), _lib.ptr(y), _lib.ptr(nz), _lib.ptr(q_off),
+                  params[0 if t == 0 else 1].ctypes.data, _HALF_LOG_2PI, seed, t, B, K, _lib.ptr(u_dev),
+                  _lib.ptr(x_new), _lib.ptr(log_w), _lib.ptr(lses[t]), _lib.ptr(idx), _lib.ptr(x_out),
+                  _lib.ptr(flags), mode)
+        if keep_originals:
+            originals.append(x_new)
+        if return_log_weights:
+            log_weights.append(log_w)
+        if not last and keep_index:
+            ancestors.append(idx)
+        x_prev = x_out
+        x_last = x_new
+    result = dict.fromkeys(("log_marginal_likelihood", "latents", "original_latents", "log_weight", "log_weights",
+                            "ancestral_indices"))
+    if return_log_marginal_likelihood:
+        result["log_marginal_likelihood"] = (lses - math.log(K)).sum(dim=0)  # inference.py:130-132
+    if return_latents:
+        result["latents"] = inference._trace_genealogy(originals, ancestors, dev)
+    if return_original_latents:
+        result["original_latents"] = originals
+    if return_log_weight:
+        result["log_weight"] = log_w
+    if return_log_weights:
+        result["log_weights"] = log_weights
+    if return_ancestral_indices:
+        result["ancestral_indices"] = [_ops.widen_index(i) for i in ancestors]
+    result["last_latent"] = x_last
+    if check_finite:
+        _ops.raise_on_flags(flags)
+    return result

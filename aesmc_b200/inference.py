@@ -32,6 +32,7 @@ import numpy as np
 import torch
 
 from . import _ops
+from . import fused
 from . import state
 from ._ops import get_resampling_mode, set_resampling_mode  # noqa: F401  (re-exported)
 
@@ -111,6 +112,15 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
     T = len(observations)
     B = _first_tensor(observations[0]).size(0)
     K = num_particles
+    if smc:
+        # models of the fused family (aesmc_b200.fused) run with their sampling and log-densities inside
+        # the step kernel; everything else takes the generic path below
+        model = fused.model_of(initial, transition, emission, proposal)
+        if fused.applicable(model, observations, K):
+            return fused.infer_fused(model, observations, K, return_log_marginal_likelihood, return_latents,
+                                     return_original_latents, return_log_weight, return_log_weights,
+                                     return_ancestral_indices, uniforms=uniforms, resampling_mode=resampling_mode,
+                                     check_finite=check_finite)
     keep_originals = return_original_latents or return_latents
 
     def draw_uniforms(t):

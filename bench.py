@@ -11,8 +11,9 @@ scalar latent (D = 1), float32.  One bench "step" = one full pass of the hot pat
            gather) + the log-evidence reduction, on synthetic log-prob tensors already resident in HBM
            (a ring of 4 x 192 MiB input sets, larger than the 126 MB L2, so nothing is served from cache)
     e2e    aesmc_b200.inference.infer('smc', ...) -- the public API a user calls -- on the bootstrap-filter
-           LGSSM user model (torch eager), with the observations [T,B] in pinned HOST memory copied H2D
-           inside the timed region and the log-evidence [B] copied back D2H
+           LGSSM, with the observations [T,B] in pinned HOST memory copied H2D inside the timed region and
+           the log-evidence [B] copied back D2H; `e2e` uses a model of the fused family (evaluated inside
+           the step kernel), `e2e_eager` the same model written as plain torch callables
 Rows are independent SMC problems, so ranks shard the batch axis with no data-path collective
 ("scaling": "weak": every rank processes B rows).
 """
@@ -197,47 +198,58 @@ def run_native(args):
                 "bytes_per_launch": bytes_per_launch, "launch_ms": round(kernel_ms, 4), "peak_source": peak_src}
 
     # ---- e2e: public infer() with host observation buffers -----------------------------------
-    e2e = None
+    # Same model (BASELINE config 2 bootstrap-filter LGSSM), same public call, two kinds of user model:
+    #   e2e        aesmc_b200.fused.ScalarLinearGaussianSSM -- infer() recognises it and evaluates the model
+    #              inside the step kernel (one launch per time step)
+    #   e2e_eager  plain torch callables (tests/models/lgssm.py) -- ~25 torch elementwise kernels per step
+    e2e = e2e_eager = None
     if not args.no_e2e:
+        from aesmc_b200 import fused
         ys = lgssm.simulate(T, B, seed=100 + rank)
         obs_host = torch.from_numpy(ys).pin_memory()
         u_host = torch.from_numpy(np.random.default_rng(7 + rank).random((T - 1, B))).pin_memory()
         out_host = torch.empty(B, dtype=torch.float32).pin_memory()
-        models = lgssm.bootstrap_filter(device=dev)
         # production setting for torch.distributions: argument/sample validation reads a device flag on
         # the host for every distribution built and every log_prob (7 synchronisations per time step)
         torch.distributions.Distribution.set_default_validate_args(False)
         del log_w, idx
         torch.cuda.empty_cache()
 
-        def e2e_pass():
-            obs = obs_host.to(dev, non_blocking=True)
-            uu = u_host.to(dev, non_blocking=True)
-            with torch.no_grad():
-                res = inference.infer("smc", obs, *models, K, return_log_marginal_likelihood=True,
-                                      return_latents=False, return_log_weight=False, uniforms=uu,
-                                      resampling_mode=mode)
-            out_host.copy_(res["log_marginal_likelihood"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        def measure(models, reps, label):
+            def one_pass():
+                obs = obs_host.to(dev, non_blocking=True)
+                uu = u_host.to(dev, non_blocking=True)
+                with torch.no_grad():
+                    res = inference.infer("smc", obs, *models, K, return_log_marginal_likelihood=True,
+                                          return_latents=False, return_log_weight=False, uniforms=uu,
+                                          resampling_mode=mode)
+                out_host.copy_(res["log_marginal_likelihood"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
-        for _ in range(2):
-            e2e_pass()
+            for _ in range(2):
+                one_pass()
+            barrier_sync(world)
+            t0 = time.perf_counter()
+            e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_start.record()
+            for _ in range(reps):
+                one_pass()
+            e_stop.record()
+            barrier_sync(world)
+            sec = max(time.perf_counter() - t0, e_start.elapsed_time(e_stop) / 1e3)
+            sec = max_over_ranks(sec, world, dev)
+            assert bool(np.isfinite(out_host.numpy()).all())
+            return {"value": world * B * K * T / (sec / reps), "unit": UNIT,
+                    "h2d_bytes_per_step": obs_host.numel() * 4 + u_host.numel() * 8, "d2h_bytes_per_step": B * 4,
+                    "ms_per_step": sec * 1e3 / reps, "steps": reps, "api": label}
+
         reps = max(1, min(args.steps, 5))
-        barrier_sync(world)
-        t0 = time.perf_counter()
-        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_start.record()
-        for _ in range(reps):
-            e2e_pass()
-        e_stop.record()
-        barrier_sync(world)
-        e_seconds = max(time.perf_counter() - t0, e_start.elapsed_time(e_stop) / 1e3)
-        e_seconds = max_over_ranks(e_seconds, world, dev)
-        e2e = {"value": world * B * K * T / (e_seconds / reps), "unit": UNIT,
-               "h2d_bytes_per_step": obs_host.numel() * 4 + u_host.numel() * 8, "d2h_bytes_per_step": B * 4,
-               "ms_per_step": e_seconds * 1e3 / reps, "steps": reps,
-               "api": "aesmc_b200.inference.infer('smc', bootstrap LGSSM user model in torch eager, "
-                      "Distribution.set_default_validate_args(False))"}
+        fused_model = fused.ScalarLinearGaussianSSM(0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 0.0, 0.5, device=dev)
+        e2e = measure(fused_model.callables(), reps,
+                      "aesmc_b200.inference.infer('smc') on fused.ScalarLinearGaussianSSM (model evaluated in the step kernel)")
+        e2e_eager = measure(lgssm.bootstrap_filter(device=dev), reps,
+                            "aesmc_b200.inference.infer('smc') on torch-eager user callables, "
+                            "Distribution.set_default_validate_args(False)")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample ---------
     cpu_baseline = None
@@ -252,7 +264,7 @@ def run_native(args):
                                        % (B, K, T, D), "resampling_mode": mode, "parallelism": "batch rows sharded, dp%d" % world,
                            "l2": "inputs ring %d x %d MiB > 126 MB L2; no flush needed" % (RING, 3 * B * K * 4 >> 20)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(), "e2e": e2e,
-                "gpu_launches": launches}
+                "e2e_eager": e2e_eager, "gpu_launches": launches}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

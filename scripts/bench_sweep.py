@@ -1,0 +1,79 @@
+"""BASELINE config 5: resampling-bound sweep of the core step, K = 1e3 ... 1e6 particles per row, small
+batch (and the headline shape for comparison).  Prints one JSON line per (B, K, mode):
+
+    python scripts/bench_sweep.py [--steps 20] > profiles/r1_sweep.jsonl
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aesmc_b200 import _lib, _ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=20)   # T
+ap.add_argument("--cpu", action="store_true", help="also time the C oracle (1 thread) on 2 rows")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+peak = 6550.1
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+T = args.steps
+for B, K in [(8, 1000), (64, 1000), (8, 10000), (64, 10000), (8, 100000), (64, 100000), (8, 1000000), (64, 1000000),
+             (4096, 1024), (1024, 16384), (4096, 4096)]:
+    gen = torch.Generator(device=dev).manual_seed(0)
+    ring = [[torch.randn(B, K, device=dev, generator=gen) - 1.4 for _ in range(3)] for _ in range(2)]
+    arena = [torch.randn(B, K, device=dev, generator=gen), torch.empty(B, K, device=dev)]
+    u = torch.rand(T, B, dtype=torch.float64, device=dev, generator=gen)
+    log_w = torch.empty(B, K, device=dev)
+    lse = torch.empty(B, device=dev)
+    idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+    flags = _ops.new_flags(dev)
+    ws_bytes = int(_lib.load().aesmc_smc_step_workspace_bytes(B, K))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    for mode in ("exact", "fast"):
+        code = _ops.mode_code(mode)
+
+        def run():
+            for t in range(T):
+                a, b, c = ring[t & 1]
+                _lib.call("aesmc_smc_step_ws_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), u[t].data_ptr(), B, K,
+                          log_w.data_ptr(), lse.data_ptr(), idx.data_ptr(), arena[t & 1].data_ptr(),
+                          arena[(t + 1) & 1].data_ptr(), 1, flags.data_ptr(), code, ws.data_ptr() if ws_bytes else None, ws_bytes)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * T)
+        gbs = 28.0 * B * K / (ms * 1e-3) / 1e9
+        line = {"B": B, "K": K, "T": T, "mode": mode, "us_per_step": round(ms * 1e3, 2),
+                "particle_steps_per_s": B * K / (ms * 1e-3), "algorithmic_GBps": round(gbs, 1),
+                "frac_of_measured_hbm": round(gbs / peak, 4), "path": "multi-CTA" if ws_bytes else "single-CTA",
+                "flags": int(flags.item())}
+        print(json.dumps(line), flush=True)
+    if args.cpu and K >= 1000 and B == 8:
+        from oracle import core as oracle
+        rng = np.random.default_rng(0)
+        rows = 2
+        a, b, c = [(rng.standard_normal((1, rows, K)) - 1.4).astype(np.float32) for _ in range(3)]
+        x = rng.standard_normal((rows, K, 1)).astype(np.float32)
+        uu = rng.random((T, rows))
+        t0 = time.perf_counter()
+        oracle.core_pass(a, b, c, uu, x, T)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"K": K, "mode": "cpu oracle (C, 1 thread)", "particle_steps_per_s": rows * K * T / dt}), flush=True)
+    del ring, arena, log_w, idx, ws
+    torch.cuda.empty_cache()

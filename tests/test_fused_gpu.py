@@ -1,0 +1,109 @@
+"""Fused-model fast path (aesmc_b200.fused): the step kernel evaluates the scalar linear-Gaussian model
+itself.  With injected noise it must reproduce the generic path (torch-eager user model + step kernel)
+bit for bit; with its own Philox stream it must track the exact Kalman evidence."""
+import numpy as np
+import pytest
+import torch
+
+import aesmc_b200
+from aesmc_b200 import fused, inference
+from oracle import kalman
+from tests.models import lgssm
+
+pytestmark = pytest.mark.gpu
+
+AFFINE = dict(p0_y=0.7, p0_off=0.1, p0_scale=0.8, pt_x=0.5, pt_y=0.4, pt_off=-0.05, pt_scale=0.6)
+
+
+def eager_with_noise(model, obs, K, noise, u, **kw):
+    """Generic path, every Normal.rsample fed from `noise` (t-th draw = noise[t], transposed when the
+    distribution is batch-expanded and therefore sampled as [K, B])."""
+    import torch.distributions.normal as tdn
+    it = iter(noise)
+    orig = tdn._standard_normal
+
+    def fake(shape, dtype, device):
+        z = next(it)
+        return z if tuple(shape) == tuple(z.shape) else z.t().contiguous()
+
+    tdn._standard_normal = fake
+    try:
+        with torch.no_grad():
+            # the lambdas hide the bound methods, so infer() takes the generic path
+            return inference.infer("smc", obs, lambda: model.initial(), lambda **k: model.transition(**k),
+                                   lambda **k: model.emission(**k), lambda **k: model.proposal(**k), K, uniforms=u, **kw)
+    finally:
+        tdn._standard_normal = orig
+
+
+@pytest.mark.parametrize("proposal", ["bootstrap", AFFINE])
+@pytest.mark.parametrize("K", [256, 4096])
+def test_fused_equals_generic_path_bitwise(cuda, proposal, K):
+    T, B = 7, 5
+    model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device=cuda)
+    obs = torch.from_numpy(lgssm.simulate(T, B, seed=1)).to(cuda)
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    noise = torch.randn(T, B, K, device=cuda, generator=gen)
+    u = np.random.default_rng(0).random((T - 1, B))
+    kw = dict(return_log_marginal_likelihood=True, return_latents=True, return_original_latents=True,
+              return_log_weight=True, return_log_weights=True, return_ancestral_indices=True)
+    ref = eager_with_noise(model, obs, K, noise, u, **kw)
+    with torch.no_grad():
+        got = fused.infer_fused(model, obs, K, uniforms=u, noise=noise, **kw)
+    for t in range(T):
+        assert torch.equal(got["original_latents"][t], ref["original_latents"][t]), ("latent", t)
+        assert torch.equal(got["log_weights"][t], ref["log_weights"][t]), ("log_w", t)
+        assert torch.equal(got["latents"][t], ref["latents"][t])
+    for a, b in zip(got["ancestral_indices"], ref["ancestral_indices"]):
+        assert torch.equal(a, b)
+    assert torch.equal(got["log_marginal_likelihood"], ref["log_marginal_likelihood"])
+    assert torch.equal(got["log_weight"], ref["log_weight"]) and torch.equal(got["last_latent"], ref["last_latent"])
+
+
+def test_infer_dispatches_to_fused_and_tracks_kalman(cuda):
+    T, B, K = 50, 16, 4096
+    ys = lgssm.simulate(T, B, seed=9)
+    exact = kalman.lgssm1d_log_evidence(ys, 0.0, 1.0, 0.9, 1.0, 1.0, 0.25)
+    model = fused.ScalarLinearGaussianSSM(0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 0.0, 0.5, device=cuda)
+    obs = torch.from_numpy(ys).to(cuda)
+    assert fused.applicable(fused.model_of(*model.callables()), obs, K)
+    launches = aesmc_b200._lib.launch_count()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    with torch.no_grad():
+        res = inference.infer("smc", obs, *model.callables(), K, return_log_marginal_likelihood=True, return_latents=False)
+    assert aesmc_b200._lib.launch_count() - launches == T        # one launch per time step, nothing else
+    err = np.abs(res["log_marginal_likelihood"].cpu().numpy() - exact)
+    print("fused bootstrap filter: max |log Z_hat - log Z| =", err.max())
+    assert err.max() < 1.0 and err.mean() < 0.35      # O(sqrt(T/K)) per row (0.64 max at K = 1000)
+    assert res["log_weight"].shape == (B, K) and res["latents"] is None
+    # different torch seed -> different Philox stream; same seed -> identical result
+    torch.manual_seed(1); np.random.seed(0)
+    with torch.no_grad():
+        r1 = inference.infer("smc", obs, *model.callables(), K, return_log_marginal_likelihood=True, return_latents=False)
+    torch.manual_seed(1); np.random.seed(0)
+    with torch.no_grad():
+        r2 = inference.infer("smc", obs, *model.callables(), K, return_log_marginal_likelihood=True, return_latents=False)
+    assert torch.equal(r1["log_marginal_likelihood"], r2["log_marginal_likelihood"])
+    assert not torch.equal(r1["log_marginal_likelihood"], res["log_marginal_likelihood"])
+
+
+def test_philox_normals_are_standard(cuda):
+    model = fused.ScalarLinearGaussianSSM(0.0, 1.0, device=cuda)
+    obs = torch.zeros(1, 64, device=cuda)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        x = fused.infer_fused(model, obs, 16384, return_latents=False)["last_latent"].double().flatten()
+    n = x.numel()
+    assert abs(x.mean().item()) < 5 / np.sqrt(n) and abs(x.var().item() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((x ** 4).mean().item() - 3) < 0.05 and abs((x ** 3).mean().item()) < 0.02
+    assert x.unique().numel() > 0.99 * n
+
+
+def test_fused_model_runs_through_generic_path_and_reference_conventions(cuda):
+    # not applicable (CPU observations / odd K): the same callables take the generic path
+    model = fused.ScalarLinearGaussianSSM(device=cuda)
+    obs = [torch.randn(3, device=cuda) for _ in range(4)]
+    res = inference.infer("smc", obs, *model.callables(), 10)
+    assert res["log_weight"].shape == (3, 10)
+    assert fused.model_of(model.initial, model.transition, model.emission, lambda **k: None) is None
