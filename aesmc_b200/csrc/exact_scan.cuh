@@ -86,13 +86,13 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     const float scale = __int_as_float((277 - (eb ? eb : 127)) << 23); // 2^(23 - e), exact multiplier
     int c0 = 0, c1 = 0;
     if (eb) {
-        float m0 = 8388608.0f, m1 = 8388609.0f; // 2^23, 2^23 + 1: ulp 1, so RN == round-half-even to integer
+        // (m0, m1) = (2^23, 2^23 + 1): ulp 1, so RN == round-half-even to integer; both parities advance
+        // in one packed FADD2 per particle
+        f32x2 m01 = pack2(8388608.0f, 8388609.0f);
 #pragma unroll
-        for (int j = 0; j < kScanItems; ++j) {
-            const float y = __fmul_rn(w[j], scale);
-            m0 = __fadd_rn(m0, y);
-            m1 = __fadd_rn(m1, y);
-        }
+        for (int j = 0; j < kScanItems; ++j) m01 = add2(m01, splat2(__fmul_rn(w[j], scale)));
+        float m0, m1;
+        unpack2(m01, m0, m1);
         if (m1 < 16777216.0f) { // still in the ulp-1 regime (always true for a genuinely pure block)
             c0 = __float_as_int(m0) & 0x7fffff;
             c1 = (__float_as_int(m1) & 0x7fffff) - 1;

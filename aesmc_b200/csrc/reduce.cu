@@ -211,14 +211,28 @@ __global__ void selftest_expf_kernel(unsigned long long *out)
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
         const unsigned bits = (i == n) ? 0xFF800000u : (0x80000000u + (unsigned)i);
         const float x = __uint_as_float(bits);
-        if (__float_as_uint(np_expf_nonpos(x)) != __float_as_uint(np_expf(x))) { ++bad; where = bits; }
+        const float want = np_expf(x);
+        // the packed pair version, with this input in either slot next to an unrelated value
+        float p0, p1, q0, q1;
+        const float other = __uint_as_float(0x80000000u + (unsigned)((i * 2654435761ull) % n));
+        np_expf_nonpos_pair(x, other, p0, p1);
+        np_expf_nonpos_pair(other, x, q0, q1);
+        const float s = np_expf_nonpos(x);
+        if (__float_as_uint(s) != __float_as_uint(want) || __float_as_uint(p0) != __float_as_uint(want) ||
+            __float_as_uint(q1) != __float_as_uint(want)) {
+            ++bad;
+            where = bits;
+            out[2] = ((unsigned long long)__float_as_uint(want) << 32) | __float_as_uint(s);
+            out[3] = ((unsigned long long)__float_as_uint(p0) << 32) | __float_as_uint(q1);
+            out[4] = __float_as_uint(other);
+        }
     }
     if (bad) { atomicAdd(out, bad); atomicExch(out + 1, where); }
 }
 
 int launch_selftest_expf(unsigned long long *out, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(out, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(out, 0, 40, st);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     selftest_expf_kernel<<<148 * 16, 256, 0, st>>>(out);
     count_launch();
