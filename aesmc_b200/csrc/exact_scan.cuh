@@ -137,7 +137,9 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     __syncthreads();
 
     // ---- one thread walks the segments: O(1) per pure run, 16 float additions per mixed block -----
-    if (tid == 0) {
+    // (lane 0 of the LAST warp: the warp scheduler favours the highest warp id among eligible warps, and
+    // every other warp is about to wait at the barrier for this chain)
+    if (tid == NT - 32) {
         float s = s_in;
         int fail = 0;
         const int nseg = sh.nseg;
