@@ -210,9 +210,10 @@ def logsumexp_rows(lw, flags=None):
     return _LogSumExp.apply(lw, flags)
 
 
-def is_accumulate(a, b, c, acc, first):
-    _lib.call("aesmc_is_accumulate_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(acc), None, a.numel(),
-              int(first))
+def is_accumulate(a, b, c, acc, log_w, first):
+    """acc (+)= (a + b) - c elementwise, log_w receives the per-step term (importance sampling)."""
+    _lib.call("aesmc_is_accumulate_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(acc), _lib.ptr(log_w),
+              a.numel(), int(first))
 
 
 def lognormexp_rows(lw, exponentiate):

@@ -158,9 +158,16 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
             log_weights.append(log_w)
             lses.append(lse)
             return idx, x_res
-        log_w, _, _, _ = _ops.smc_step(a, b, c, None, None, flags, resampling_mode, resample=False)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (a, b, c)):
+            log_w, _, _, _ = _ops.smc_step(a, b, c, None, None, flags, resampling_mode, resample=False)
+            total = log_w if total is None else total + log_w  # inference.py:156 (sequential over t)
+        else:  # one pass: log_w = (a + b) - c and total += log_w (aesmc_is_accumulate_f32)
+            log_w = torch.empty_like(a)
+            first = total is None
+            if first:
+                total = torch.empty_like(a)
+            _ops.is_accumulate(a, b, c, total, log_w, first)
         log_weights.append(log_w)
-        total = log_w if total is None else total + log_w  # inference.py:156 (sequential over t)
         return None, None
 
     # ---- t = 1 .. T-1 (inference.py:99-126) -------------------------------------------------
