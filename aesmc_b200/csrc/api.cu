@@ -35,8 +35,8 @@ int launch_smc_step(const float *, const float *, const float *, const double *,
 int64_t step_workspace_bytes(int64_t B, int64_t K);
 bool smc_step_lg_supported(int64_t K);
 int launch_smc_step_lg(const float *, const float *, const float *, const float *, const float *, float,
-                       unsigned long long, unsigned long long, int64_t, int64_t, const double *, float *, float *,
-                       float *, int32_t *, float *, int32_t *, int, cudaStream_t);
+                       unsigned long long, const unsigned long long *, unsigned long long, int64_t, int64_t,
+                       const double *, float *, float *, float *, int32_t *, float *, int32_t *, int, cudaStream_t);
 int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
 int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
 int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
@@ -109,9 +109,9 @@ int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_
 }
 
 int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
-                          const float *params_host, float half_log_2pi, uint64_t seed, uint64_t stream_offset,
-                          int64_t B, int64_t K, const double *u, float *x_new, float *log_w, float *lse, int32_t *idx,
-                          float *x_out, int32_t *flags, int mode, void *stream)
+                          const float *params_host, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
+                          uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
+                          float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream)
 {
     const char *fn = "aesmc_smc_step_lg_f32";
     REQUIRE(y && params_host && flags, fn);
@@ -128,8 +128,9 @@ int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *nois
                            reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(x_out);
     REQUIRE((bits & 15) == 0, fn);
     if (B == 0) return AESMC_OK;
-    return launch_smc_step_lg(x_prev, y, noise, q_off, params_host, half_log_2pi, seed, stream_offset, B, K, u, x_new,
-                              log_w, lse, idx, x_out, flags, mode, S(stream));
+    return launch_smc_step_lg(x_prev, y, noise, q_off, params_host, half_log_2pi, seed,
+                              reinterpret_cast<const unsigned long long *>(seed_dev), stream_offset, B, K, u, x_new, log_w,
+                              lse, idx, x_out, flags, mode, S(stream));
 }
 
 int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,

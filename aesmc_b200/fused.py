@@ -156,7 +156,7 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
             x_out = arena[t & 1]
         nz = None if noise is None else noise[t].contiguous()
         _lib.call("aesmc_smc_step_lg_f32", _lib.ptr(x_prev), _lib.ptr(y), _lib.ptr(nz), _lib.ptr(q_off),
-                  params[0 if t == 0 else 1].ctypes.data, _HALF_LOG_2PI, seed, t, B, K, _lib.ptr(u_dev),
+                  params[0 if t == 0 else 1].ctypes.data, _HALF_LOG_2PI, seed, None, t, B, K, _lib.ptr(u_dev),
                   _lib.ptr(x_new), _lib.ptr(log_w), _lib.ptr(lses[t]), _lib.ptr(idx), _lib.ptr(x_out),
                   _lib.ptr(flags), mode)
         if keep_originals:
@@ -185,3 +185,87 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
     if check_finite:
         _ops.raise_on_flags(flags)
     return result
+
+
+class GraphedFilter:
+    """The T-step bootstrap / guided particle filter of a ScalarLinearGaussianSSM captured ONCE as a CUDA
+    graph (T fused-step launches, device-side uniforms, the evidence reduction) and replayed per batch of
+    observation sequences: no per-step Python, launch or allocation cost -- what makes small problems
+    (BASELINE config 1: B = 1, K = 100, T = 50) launch-latency-free.
+
+        f = GraphedFilter(model, num_timesteps=T, batch_size=B, num_particles=K)
+        log_evidence = f(observations)          # [T, B] float32 tensor (host or device) -> [B]
+
+    Every replay advances the Philox key (a device-resident counter) and draws fresh resampling uniforms
+    with torch's graph-safe generator.  `noise` / `uniforms` buffers can be filled for tests
+    (inject_noise=True).  Degenerate-weight flags accumulate in `self.flags` (check with `check()`)."""
+
+    def __init__(self, model, num_timesteps, batch_size, num_particles, resampling_mode=None, inject_noise=False):
+        first = torch.empty(batch_size, dtype=torch.float32, device=model.m0.device)
+        if not applicable(model, [first], num_particles):
+            raise ValueError("GraphedFilter needs a CUDA ScalarLinearGaussianSSM and 64 <= K <= 16384, K % 4 == 0")
+        T, B, K = num_timesteps, batch_size, num_particles
+        dev = model.m0.device
+        self.model, self.T, self.B, self.K = model, T, B, K
+        self.obs = torch.zeros(T, B, dtype=torch.float32, device=dev)
+        self.uniforms = torch.zeros(max(T - 1, 1), B, dtype=torch.float64, device=dev)
+        self.noise = torch.zeros(T, B, K, dtype=torch.float32, device=dev) if inject_noise else None
+        self.lses = torch.zeros(T, B, dtype=torch.float32, device=dev)
+        self.log_weight = torch.empty(B, K, dtype=torch.float32, device=dev)
+        self.last_latent = torch.empty(B, K, dtype=torch.float32, device=dev)
+        self.flags = _ops.new_flags(dev)
+        self.seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
+        self._arena = [torch.empty(B, K, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+        self._q_off = None if model.prop is None else torch.empty(T, B, dtype=torch.float32, device=dev)
+        self._params = model.kernel_params()
+        self._mode = _ops.mode_code(resampling_mode)
+        self._inject = inject_noise
+        self.log_evidence = torch.empty(B, dtype=torch.float32, device=dev)
+        # warm-up on a side stream (loads the module, sets function attributes), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.flags.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+
+    def _body(self):
+        model, T, B, K = self.model, self.T, self.B, self.K
+        if not self._inject:
+            self.seed.add_(1)
+            self.uniforms.copy_(torch.rand(self.uniforms.shape, dtype=torch.float64, device=self.uniforms.device))
+        if self._q_off is not None:
+            self._q_off[0].copy_(self.obs[0] * model.prop["p0_y"] + model.prop["p0_off"])
+            if T > 1:
+                self._q_off[1:].copy_(self.obs[1:] * model.prop["pt_y"] + model.prop["pt_off"])
+        x_prev = None
+        for t in range(T):
+            last = t == T - 1
+            x_out = None if last else self._arena[t & 1]
+            _lib.call("aesmc_smc_step_lg_f32", _lib.ptr(x_prev), _lib.ptr(self.obs[t]),
+                      _lib.ptr(None if self.noise is None else self.noise[t]),
+                      _lib.ptr(None if self._q_off is None else self._q_off[t]),
+                      self._params[0 if t == 0 else 1].ctypes.data, _HALF_LOG_2PI, 0,
+                      None if self._inject else _lib.ptr(self.seed), t, B, K,
+                      None if last else _lib.ptr(self.uniforms[t]), _lib.ptr(self.last_latent) if last else None,
+                      _lib.ptr(self.log_weight) if last else None, _lib.ptr(self.lses[t]),
+                      None if last else _lib.ptr(self._idx), _lib.ptr(x_out), _lib.ptr(self.flags), self._mode)
+            x_prev = x_out
+        self.log_evidence.copy_((self.lses - math.log(K)).sum(dim=0))
+
+    def __call__(self, observations, clone=True):
+        """observations: [T, B] float32 tensor (any device) or list of T tensors [B]."""
+        if not torch.is_tensor(observations):
+            observations = torch.stack(list(observations))
+        self.obs.copy_(observations, non_blocking=True)
+        self.graph.replay()
+        return self.log_evidence.clone() if clone else self.log_evidence
+
+    def check(self):
+        """Host read of the accumulated NaN / degenerate-row flags (raises like inference.infer)."""
+        _ops.raise_on_flags(self.flags)

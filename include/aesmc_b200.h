@@ -91,15 +91,16 @@ int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_
  *                        - log N(x; q.mult*x_prev + q_off[b], q.scale^2)
  * then lse / systematic ancestors / gather of x exactly as aesmc_smc_step_f32.
  *   x_prev [B,K] resampled latents of the previous step (NULL at t = 0: treated as 0)
- *   y [B]; noise [B,K] injected standard normals or NULL (Philox4x32-10 keyed by seed, stream_offset)
+ *   y [B]; noise [B,K] injected standard normals or NULL (Philox4x32-10 keyed by seed, stream_offset;
+ *   seed_dev non-NULL: the key is read from device memory at run time, for CUDA-graph replays)
  *   q_off [B] per-row proposal offset or NULL (then the proposal's scalar offset)
  *   params_host: HOST pointer to 15 floats = (mult, off, scale, 2*scale^2, log scale) for t, e, q
  *   x_new, log_w: optional outputs (proposed latents, log-weights); idx/x_out both NULL to skip resampling
  */
 int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
-                          const float *params_host, float half_log_2pi, uint64_t seed, uint64_t stream_offset,
-                          int64_t B, int64_t K, const double *u, float *x_new, float *log_w, float *lse,
-                          int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream);
+                          const float *params_host, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
+                          uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
+                          float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream);
 
 /*
  * Resampling entered at a later stage (used by the staged parity tests, and useful on their own):

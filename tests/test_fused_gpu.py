@@ -107,3 +107,43 @@ def test_fused_model_runs_through_generic_path_and_reference_conventions(cuda):
     res = inference.infer("smc", obs, *model.callables(), 10)
     assert res["log_weight"].shape == (3, 10)
     assert fused.model_of(model.initial, model.transition, model.emission, lambda **k: None) is None
+
+
+@pytest.mark.parametrize("proposal", ["bootstrap", AFFINE])
+def test_graphed_filter_equals_stepwise_path(cuda, proposal):
+    """The CUDA-graph replay of the T-step filter == infer_fused step by step (injected noise/uniforms)."""
+    T, B, K = 9, 4, 512
+    model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device=cuda)
+    f = fused.GraphedFilter(model, T, B, K, inject_noise=True)
+    gen = torch.Generator(device=cuda).manual_seed(1)
+    for rep in range(2):
+        obs = torch.randn(T, B, device=cuda, generator=gen)
+        noise = torch.randn(T, B, K, device=cuda, generator=gen)
+        u = torch.rand(T - 1, B, dtype=torch.float64, device=cuda, generator=gen)
+        f.noise.copy_(noise)
+        f.uniforms.copy_(u)
+        got = f(obs.cpu())                      # host observations are copied in
+        with torch.no_grad():
+            ref = fused.infer_fused(model, obs, K, return_log_marginal_likelihood=True, return_latents=False,
+                                    uniforms=u, noise=noise)
+        assert torch.equal(got, ref["log_marginal_likelihood"])
+        assert torch.equal(f.log_weight, ref["log_weight"]) and torch.equal(f.last_latent, ref["last_latent"])
+    f.check()
+
+
+def test_graphed_filter_fresh_randomness_and_kalman(cuda):
+    T, B, K = 50, 8, 4096
+    ys = lgssm.simulate(T, B, seed=4)
+    exact = kalman.lgssm1d_log_evidence(ys, 0.0, 1.0, 0.9, 1.0, 1.0, 0.25)
+    model = fused.ScalarLinearGaussianSSM(0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 0.0, 0.5, device=cuda)
+    torch.manual_seed(0)
+    f = fused.GraphedFilter(model, T, B, K)
+    obs = torch.from_numpy(ys)
+    runs = torch.stack([f(obs) for _ in range(8)]).cpu().numpy()
+    assert len({r.tobytes() for r in runs}) == 8                # every replay uses new noise and uniforms
+    assert np.abs(runs.mean(axis=0) - exact).max() < 0.5        # averaged over replays the bias is small
+    f.check()
+    # BASELINE config 1 shape (B = 1, K = 100, T = 50): one replay, no per-step host work
+    small = fused.GraphedFilter(model, 50, 1, 100)
+    out = small(torch.from_numpy(ys[:, :1]))
+    assert out.shape == (1,) and torch.isfinite(out).all()
