@@ -109,6 +109,8 @@ def log_prob(distribution, value):
     else:
         raise RuntimeError("Incompatible distribution.batch_shape ({}) and value.shape ({}).".format(
             distribution.batch_shape, value.shape))
+    if lp.dim() == 2:  # no event / extra dims to reduce: skip the [B, K, 1] sum (a full copy of the table)
+        return lp
     return lp.reshape(value.size(0), value.size(1), -1).sum(dim=2)
 
 
