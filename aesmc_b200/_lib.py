@@ -38,6 +38,10 @@ _PROTOTYPES = {
     "aesmc_iota_index_i32": [_i64, _i64, _vp, _vp],
     "aesmc_index_widen": [_vp, _vp, _i64, _vp],
     "aesmc_index_narrow": [_vp, _vp, _i64, _vp],
+    "aesmc_normal_log_prob_f32": [_vp, _int, _vp, _int, ctypes.c_float, _vp, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, _i64, _i64, _vp, _vp],
+    "aesmc_normal_log_prob_bwd_f32": [_vp, _int, _vp, _int, ctypes.c_float, _vp, ctypes.c_float, _vp, _i64, _i64, _vp, _vp,
+                                      _vp, _vp],
     "aesmc_selftest_expf": [_vp, _vp],
     "aesmc_log_ess_f32": [_vp, _i64, _i64, _vp, _vp],
     "aesmc_log_ess_f64": [_vp, _i64, _i64, _vp, _vp],

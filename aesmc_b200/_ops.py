@@ -241,6 +241,100 @@ def weighted_moments(x, lw, want_second=True):
     return mean, second
 
 
+# ------------------------------------------------------------------------------------------------
+# torch.distributions.Normal.log_prob in one kernel (bit-identical to torch's elementwise sequence)
+# ------------------------------------------------------------------------------------------------
+_HALF_LOG_2PI = float(np.float32(np.log(np.sqrt(2 * np.pi))))
+
+
+def _compact(t, B, K):
+    """(compact differentiable view, kind) of a tensor that broadcasts against a [B, K] table:
+    kind 0 = [B, K] contiguous, 1 = one value per row [B], 2 = a single element; None if neither."""
+    if t.dim() == 0:
+        return t, 2
+    if t.dim() == 1 and t.shape[0] == B:
+        return (t[0], 2) if (t.stride(0) == 0 and B > 1) else (t, 1)
+    if t.dim() == 2 and tuple(t.shape) == (B, K):
+        s0, s1 = t.stride()
+        if s0 == 0 and s1 == 0:
+            return t[0, 0], 2
+        if s1 == 0:
+            return t[:, 0], 1
+        return t, 0
+    if t.dim() == 2 and tuple(t.shape) == (B, 1):
+        return t[:, 0], 1
+    return None, None
+
+
+class _NormalLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, value_kind, loc, loc_kind, scale, B, K):
+        dev = value.device
+        value = value.contiguous()
+        loc_dev = loc is not None and loc.is_cuda
+        scale_dev = scale.is_cuda
+        loc_c = loc.contiguous() if loc_dev else None
+        loc_host = 0.0 if loc_dev else float(loc)
+        if scale_dev:
+            scale_c, inv_two_var, log_scale = scale.contiguous(), 0.0, 0.0
+        else:  # CPU scalar: torch multiplies by the float32 reciprocal of (2 * var) and subtracts scale.log()
+            two_var = np.float32(2.0) * (np.float32(float(scale)) * np.float32(float(scale)))
+            scale_c, inv_two_var, log_scale = None, float(np.float32(1.0) / two_var), float(scale.log())
+        out = torch.empty((B, K), dtype=torch.float32, device=dev)
+        _lib.call("aesmc_normal_log_prob_f32", _lib.ptr(value), value_kind, _lib.ptr(loc_c), loc_kind, loc_host,
+                  _lib.ptr(scale_c), inv_two_var, log_scale, _HALF_LOG_2PI, B, K, _lib.ptr(out))
+        ctx.save_for_backward(value, loc_c, scale_c)
+        ctx.meta = (value_kind, loc_kind, loc_host, float(scale) if not scale_dev else 0.0, B, K)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        value, loc_c, scale_c = ctx.saved_tensors
+        value_kind, loc_kind, loc_host, scale_host, B, K = ctx.meta
+        need_v, need_l, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[2], ctx.needs_input_grad[4]
+        g = g.contiguous()
+        new = lambda: torch.empty((B, K), dtype=torch.float32, device=g.device)  # noqa: E731
+        gv = new() if need_v else None
+        gl = new() if need_l else None
+        gs = new() if need_s else None
+        _lib.call("aesmc_normal_log_prob_bwd_f32", _lib.ptr(value), value_kind, _lib.ptr(loc_c), loc_kind, loc_host,
+                  _lib.ptr(scale_c), scale_host, _lib.ptr(g), B, K, _lib.ptr(gv), _lib.ptr(gl), _lib.ptr(gs))
+
+        def fold(t, kind):
+            if t is None:
+                return None
+            return t if kind == 0 else (t.sum(dim=1) if kind == 1 else t.sum())
+
+        return fold(gv, value_kind), None, fold(gl, loc_kind), None, fold(gs, 2), None, None
+
+
+def normal_log_prob(distribution, value):
+    """log N(value; loc, scale) as a [B, K] table in one kernel, or None when the operands do not fit the
+    fast path (then the caller uses distribution.log_prob).  Handles value [B, K] (dense or broadcast from
+    [B]), loc dense / per-row / scalar (CUDA or CPU), scalar scale (CUDA or CPU)."""
+    if type(distribution) is not torch.distributions.Normal or value.dim() != 2:
+        return None
+    if not (value.is_cuda and value.dtype == torch.float32):
+        return None
+    B, K = value.shape
+    loc, scale = distribution.loc, distribution.scale
+    if loc.dtype != torch.float32 or scale.dtype != torch.float32:
+        return None
+    v_c, v_kind = _compact(value, B, K)
+    l_c, l_kind = _compact(loc, B, K)
+    s_c, s_kind = _compact(scale, B, K)
+    if v_c is None or l_c is None or s_kind != 2 or v_kind == 2:
+        return None
+    for t in (l_c, s_c):
+        if t.is_cuda and t.device != value.device:
+            return None
+        if not t.is_cuda and (l_kind != 2 if t is l_c else False):
+            return None
+        if not t.is_cuda and t.requires_grad:  # CPU scalar parameters: leave the autograd graph to torch
+            return None
+    return _NormalLogProb.apply(v_c, v_kind, l_c, l_kind, s_c, B, K)
+
+
 def compose_index(prev, cur):
     B, K = prev.shape
     out = torch.empty_like(prev)

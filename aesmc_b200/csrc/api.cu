@@ -54,6 +54,10 @@ int launch_iota_index(int64_t, int64_t, int32_t *, cudaStream_t);
 int launch_index_widen(const int32_t *, int64_t *, int64_t, cudaStream_t);
 int launch_index_narrow(const int64_t *, int32_t *, int64_t, cudaStream_t);
 int launch_selftest_expf(unsigned long long *, cudaStream_t);
+int normal_log_prob_f32(const float *, int, const float *, int, float, const float *, float, float, float, int64_t, int64_t,
+                        float *, cudaStream_t);
+int normal_log_prob_bwd_f32(const float *, int, const float *, int, float, const float *, float, const float *, int64_t,
+                            int64_t, float *, float *, float *, cudaStream_t);
 
 } // namespace aesmc
 
@@ -252,6 +256,30 @@ int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream)
     REQUIRE(in && out && n >= 0, fn);
     if (n == 0) return AESMC_OK;
     return launch_index_narrow(in, out, n, S(stream));
+}
+
+int aesmc_normal_log_prob_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                              const float *scale_dev, float inv_two_var_host, float log_scale_host, float half_log_2pi,
+                              int64_t B, int64_t K, float *out, void *stream)
+{
+    const char *fn = "aesmc_normal_log_prob_f32";
+    REQUIRE(value && out && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(value_kind >= 0 && value_kind <= 2 && loc_kind >= 0 && loc_kind <= 2, fn);
+    if (B == 0) return AESMC_OK;
+    return normal_log_prob_f32(value, value_kind, loc, loc_kind, loc_host, scale_dev, inv_two_var_host, log_scale_host,
+                               half_log_2pi, B, K, out, S(stream));
+}
+
+int aesmc_normal_log_prob_bwd_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                                  const float *scale_dev, float scale_host, const float *g, int64_t B, int64_t K,
+                                  float *g_value, float *g_loc, float *g_scale, void *stream)
+{
+    const char *fn = "aesmc_normal_log_prob_bwd_f32";
+    REQUIRE(value && g && B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
+    REQUIRE(value_kind >= 0 && value_kind <= 2 && loc_kind >= 0 && loc_kind <= 2, fn);
+    if (B == 0) return AESMC_OK;
+    return normal_log_prob_bwd_f32(value, value_kind, loc, loc_kind, loc_host, scale_dev, scale_host, g, B, K, g_value,
+                                   g_loc, g_scale, S(stream));
 }
 
 int aesmc_selftest_expf(uint64_t *out2, void *stream)

@@ -201,6 +201,68 @@ __global__ void weighted_moments_kernel(const float *__restrict__ x, const float
     }
 }
 
+// ---- torch.distributions.Normal.log_prob over a [B, K] table in ONE pass ----------------------------------
+// state.log_prob (state.py:114-155) evaluates Normal.log_prob through six torch elementwise kernels
+// (sub, pow, neg, div, sub, sub); this kernel does the same float32 operations in the same order --
+//   -((value - loc) ** 2) / (2 * var) - log_scale - log(sqrt(2 pi))
+// so the result is bit-identical.  Operand kinds: 0 = one element per particle [B*K], 1 = one element per
+// row [B] (broadcast over particles), 2 = a single element in device memory.  scale is a scalar: either a
+// device element (true IEEE division by 2*scale^2, log(scale) with logf, as torch does for a 0-dim CUDA
+// tensor) or host-supplied (inv_two_var, log_scale) -- torch multiplies by the float32 reciprocal when
+// the divisor is a CPU scalar.
+struct NormalArgs {
+    const float *value, *loc, *scale_dev;
+    int value_kind, loc_kind;
+    float loc_host, inv_two_var_host, log_scale_host, half_log_2pi;
+    int scale_on_host, loc_on_host;
+};
+
+__device__ __forceinline__ float normal_operand(const float *p, int kind, int64_t i, int64_t row)
+{
+    return kind == 0 ? p[i] : (kind == 1 ? __ldg(p + row) : __ldg(p));
+}
+
+__global__ void normal_log_prob_kernel(const NormalArgs a, int64_t n, int K, float *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float two_var = 0.f, log_scale = a.log_scale_host;
+    if (!a.scale_on_host) {
+        const float sc = __ldg(a.scale_dev);
+        two_var = __fmul_rn(2.0f, __fmul_rn(sc, sc));
+        log_scale = logf(sc);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t row = i / K;
+        const float v = normal_operand(a.value, a.value_kind, i, row);
+        const float mu = a.loc_on_host ? a.loc_host : normal_operand(a.loc, a.loc_kind, i, row);
+        const float d = __fsub_rn(v, mu);
+        const float num = -__fmul_rn(d, d);
+        const float q = a.scale_on_host ? __fmul_rn(num, a.inv_two_var_host) : __fdiv_rn(num, two_var);
+        out[i] = __fsub_rn(__fsub_rn(q, log_scale), a.half_log_2pi);
+    }
+}
+
+// backward: g_value = -g * d / var, and the per-particle terms of the loc / scale gradients
+//   g_loc_term = g * d / var          g_scale_term = g * (d^2 / scale^3 - 1 / scale)
+__global__ void normal_log_prob_bwd_kernel(const NormalArgs a, const float *__restrict__ g, float scale, int64_t n, int K,
+                                           float *__restrict__ g_value, float *__restrict__ g_loc,
+                                           float *__restrict__ g_scale)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float sc = a.scale_on_host ? scale : __ldg(a.scale_dev);
+    const float inv_var = 1.0f / (sc * sc), inv_sc = 1.0f / sc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t row = i / K;
+        const float v = normal_operand(a.value, a.value_kind, i, row);
+        const float mu = a.loc_on_host ? a.loc_host : normal_operand(a.loc, a.loc_kind, i, row);
+        const float d = v - mu, gi = g[i];
+        const float t = gi * d * inv_var;
+        if (g_value) g_value[i] = -t;
+        if (g_loc) g_loc[i] = t;
+        if (g_scale) g_scale[i] = gi * (d * d * inv_var * inv_sc - inv_sc);
+    }
+}
+
 // Exhaustive device-side check of np_expf_nonpos against np_expf over every float in [-104, -0] and
 // -inf: out[0] = number of bit mismatches, out[1] = bit pattern of one mismatching input.
 __global__ void selftest_expf_kernel(unsigned long long *out)
@@ -228,6 +290,34 @@ __global__ void selftest_expf_kernel(unsigned long long *out)
         }
     }
     if (bad) { atomicAdd(out, bad); atomicExch(out + 1, where); }
+}
+
+static unsigned flat_grid(int64_t n, int threads);
+
+int normal_log_prob_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                        const float *scale_dev, float inv_two_var_host, float log_scale_host, float half_log_2pi,
+                        int64_t B, int64_t K, float *out, cudaStream_t st)
+{
+    NormalArgs a;
+    a.value = value; a.value_kind = value_kind; a.loc = loc; a.loc_kind = loc_kind; a.loc_host = loc_host;
+    a.loc_on_host = (loc == nullptr); a.scale_dev = scale_dev; a.scale_on_host = (scale_dev == nullptr);
+    a.inv_two_var_host = inv_two_var_host; a.log_scale_host = log_scale_host; a.half_log_2pi = half_log_2pi;
+    normal_log_prob_kernel<<<flat_grid(B * K, 256), 256, 0, st>>>(a, B * K, (int)K, out);
+    count_launch();
+    return check_launch("normal_log_prob_kernel");
+}
+
+int normal_log_prob_bwd_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                            const float *scale_dev, float scale_host, const float *g, int64_t B, int64_t K,
+                            float *g_value, float *g_loc, float *g_scale, cudaStream_t st)
+{
+    NormalArgs a;
+    a.value = value; a.value_kind = value_kind; a.loc = loc; a.loc_kind = loc_kind; a.loc_host = loc_host;
+    a.loc_on_host = (loc == nullptr); a.scale_dev = scale_dev; a.scale_on_host = (scale_dev == nullptr);
+    a.inv_two_var_host = 0.f; a.log_scale_host = 0.f; a.half_log_2pi = 0.f;
+    normal_log_prob_bwd_kernel<<<flat_grid(B * K, 256), 256, 0, st>>>(a, g, scale_host, B * K, (int)K, g_value, g_loc, g_scale);
+    count_launch();
+    return check_launch("normal_log_prob_bwd_kernel");
 }
 
 int launch_selftest_expf(unsigned long long *out, cudaStream_t st)

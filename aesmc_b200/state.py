@@ -97,6 +97,13 @@ def log_prob(distribution, value):
             "distribution must be a dict or a torch.distributions.Distribution. Got: {}".format(distribution))
     lead = value.dim() - len(distribution.event_shape)  # number of batch-like dims of value
     have = len(distribution.batch_shape)
+    if lead == 2 and have in (0, 1, 2) and type(distribution) is torch.distributions.Normal and value.is_cuda:
+        # scalar Normal over a [batch, particle] table: one kernel, bit-identical to torch's six
+        if getattr(distribution, "_validate_args", True):
+            distribution._validate_sample(value if have != 1 else value.transpose(0, 1))
+        fast = _ops.normal_log_prob(distribution, value)
+        if fast is not None:
+            return fast
     if lead == have or lead == have + 2:
         # The reference validates the sample unconditionally (state.py:142), which costs a host
         # synchronisation per call on CUDA tensors; here a distribution built with

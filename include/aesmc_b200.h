@@ -155,6 +155,20 @@ int aesmc_iota_index_i32(int64_t B, int64_t K, int32_t *out, void *stream);
 int aesmc_index_widen(const int32_t *in, int64_t *out, int64_t n, void *stream);
 int aesmc_index_narrow(const int64_t *in, int32_t *out, int64_t n, void *stream);
 
+/* torch.distributions.Normal.log_prob over a [B, K] particle table in one pass, bit-identical to torch's six
+ * elementwise kernels (the log-density calls of state.py:114-155 / inference.py:88-120).  value / loc kinds:
+ * 0 = [B*K] elements, 1 = [B] (one per row), 2 = one device element; loc == NULL: loc_host.  scale is a
+ * scalar: scale_dev (device element: IEEE division by 2*scale^2, logf) or, if NULL, the host-computed
+ * float32 reciprocal inv_two_var_host and log_scale_host (torch multiplies by the reciprocal of a CPU scalar). */
+int aesmc_normal_log_prob_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                              const float *scale_dev, float inv_two_var_host, float log_scale_host, float half_log_2pi,
+                              int64_t B, int64_t K, float *out, void *stream);
+/* Its backward: per-particle gradient terms g_value = -g d/var, g_loc = g d/var, g_scale = g (d^2/scale^3 - 1/scale)
+ * (each output nullable; reductions over broadcast operands are the caller's). */
+int aesmc_normal_log_prob_bwd_f32(const float *value, int value_kind, const float *loc, int loc_kind, float loc_host,
+                                  const float *scale_dev, float scale_host, const float *g, int64_t B, int64_t K,
+                                  float *g_value, float *g_loc, float *g_scale, void *stream);
+
 /* Device self-test: compares the hot path's specialised float32 exp (non-positive arguments, custom
  * correctly-rounded division) with the general reference-order exp for EVERY float in [-104, -0] and
  * -inf.  out2: device uint64[2] = {number of mismatching inputs, bit pattern of one of them}. */
