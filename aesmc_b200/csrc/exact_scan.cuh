@@ -32,6 +32,24 @@ struct ExactScanShared {
     float wsum[32];
     int nseg, fail;
     float total;
+    float carry_in; // chained rows: the exact value the chain entered this span with
+};
+
+// Where the chain's entry value comes from.
+//   LocalCarry   : known up front (a whole row in one CTA, or spans streamed by one CTA).
+//   chained spans: a row cut into spans owned by different CTAs (smc_step_large.cu).  The blocks are
+//                  classified against an ESTIMATE of the entry value (anchor +- slack) while the
+//                  previous span is still running; the segment walker then waits for the exact carry,
+//                  checks that it lies inside the assumed band (otherwise the call fails with
+//                  sh.fail == 2 and sh.carry_in set, and the caller redoes the span with a LocalCarry),
+//                  and publishes the span's exit value as soon as it is known -- before the replay.
+struct LocalCarry {
+    static constexpr bool kChained = false;
+    float s_in;
+    __device__ __forceinline__ float anchor() const { return s_in; }
+    __device__ __forceinline__ float slack() const { return 0.f; }
+    __device__ __forceinline__ float wait() const { return s_in; }
+    __device__ __forceinline__ void publish(float) const {}
 };
 
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
@@ -47,8 +65,9 @@ __device__ __forceinline__ void compose_maps(int p0, int p1, int n0, int n1, int
 // aligned.  Returns
 // true on success with *total = cumulative sum of the whole row; false if a verification failed (w
 // is then unspecified and the caller recomputes the row with the sequential chain).
+template <class Carry>
 __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
-                                                     int *scratch, ExactScanShared &sh, float s_in = 0.f)
+                                                     int *scratch, ExactScanShared &sh, const Carry carry)
 {
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
@@ -71,11 +90,19 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     __syncthreads();
     float woff = 0.f;
     for (int v = 0; v < warp; ++v) woff += sh.wsum[v];
-    const float p_in = s_in + (woff + (incl - ls)), p_out = s_in + (woff + incl);
+    const float s_anchor = carry.anchor();
+    const float p_in = s_anchor + (woff + (incl - ls)), p_out = s_anchor + (woff + incl);
     // |chain - real prefix| <= k * 2^-24 relative (each RN adds <= 2^-24 of the running sum); the
     // float scan above adds < 64 further roundings.
     const float eps = (float)(kScanItems * (tid + 1) + 64) * 5.9604644775390625e-08f;
-    const float lo = __fmul_rd(p_in, 1.0f - eps), hi = __fmul_ru(p_out, 1.0f + eps);
+    float lo, hi;
+    if constexpr (Carry::kChained) {
+        lo = __fmul_rd(__fsub_rd(p_in, carry.slack()), 1.0f - eps);
+        hi = __fmul_ru(__fadd_ru(p_out, carry.slack()), 1.0f + eps);
+    } else {
+        lo = __fmul_rd(p_in, 1.0f - eps);
+        hi = __fmul_ru(p_out, 1.0f + eps);
+    }
     int eb = 0;
     if (lo >= 7.8886090522101181e-31f) { // 2^-100: keeps 2^(23-e) representable
         const int el = __float_as_int(lo) >> 23, eh = __float_as_int(hi) >> 23;
@@ -140,9 +167,13 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     // (lane 0 of the LAST warp: the warp scheduler favours the highest warp id among eligible warps, and
     // every other warp is about to wait at the barrier for this chain)
     if (tid == NT - 32) {
-        float s = s_in;
+        float s = carry.wait();
         int fail = 0;
-        const int nseg = sh.nseg;
+        int nseg = sh.nseg;
+        if constexpr (Carry::kChained) {
+            sh.carry_in = s;
+            if (!(fabsf(__fsub_rn(s, s_anchor)) <= carry.slack())) { fail = 2; nseg = 0; }
+        }
         seg_state[0] = s;
         int4 rec = seg_rec[0];
         for (int i = 0; i < nseg; ++i) {
@@ -164,6 +195,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
             }
             seg_state[i + 1] = s;
         }
+        if (!fail) carry.publish(s);
         sh.total = s;
         sh.fail = fail;
     }
@@ -197,6 +229,12 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     }
     *total = sh.total;
     return __syncthreads_or(bad) == 0;
+}
+
+__device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], float *total, const float4 *bufW4,
+                                                     int *scratch, ExactScanShared &sh, float s_in = 0.f)
+{
+    return exact_cumsum_blocked(w, total, bufW4, scratch, sh, LocalCarry{s_in});
 }
 
 } // namespace aesmc

@@ -6,22 +6,29 @@
 //
 //   L1 prep      log_w = (a+b)-c -> HBM, per-tile max, NaN flag                      grid (tiles, B)
 //   L2 weights   FAST : e = exp2(lw - max) -> W, per-tile sums                       grid (tiles, B)
-//                EXACT: scipy/numpy-order lse, one CTA per row (pairwise tree with    grid (B)
-//                       macro-leaves of <= 1024 particles evaluated per thread)
+//                EXACT: scipy/numpy-order lse.  numpy's pairwise-summation tree depends on K only and
+//                       is never stored (heap indices, extents recomputed from the root): its leaves
+//                       (64..128 particles, 8 lanes each) are evaluated by a (chunks, B) grid, one CTA
+//                       per row folds the levels.
 //   L3 cdf       FAST : tile scan + offset from the tile sums                        grid (tiles, B)
-//                EXACT: the reference's sequential float32 cumulative sum, streamed   grid (B)
-//                       16 384 particles at a time with the exact carry (exact_scan.cuh)
+//                EXACT: the reference's sequential float32 cumulative sum.  The row is cut into spans
+//                       of 16 384 particles owned by different CTAs (dynamic tickets, span-major): each
+//                       classifies and composes its blocks against an estimate of its entry value while
+//                       its predecessor is still running, then waits for the exact carry, walks its
+//                       ~20 segments, publishes its exit value and only then replays (exact_scan.cuh).
 //   L4 search    closed-form offspring boundaries c_j, run starts scattered into      grid (tiles, B)
 //                a zeroed [B, K] int32 mark table (atomicMax)
 //   L5 expand    one float64 binary search per tile for the ancestor entering the     grid (tiles, B)
 //                tile, max-scan of the tile's marks, idx out, ancestral gather
 //
 // Workspace (caller-allocated, aesmc_smc_step_workspace_bytes): W [B,K] f32, marks [B,K] i32, per-tile
-// max / sum [B, tiles], per-row max / total / lse.
+// max / sum [B, tiles], per-row max / total / lse, the heap of summation-tree node values of each row,
+// one 8-byte carry slot per span.
 #include "common.cuh"
 #include "pairwise.cuh"
 #include "scan.cuh"
 #include "exact_scan.cuh"
+#include <algorithm>
 
 namespace aesmc {
 
@@ -47,6 +54,12 @@ struct LargeParams {
     float *rowlse;   // [B]
     int *rowbad;     // [B] 1: NaN, 2: degenerate
     float tol32;
+    // exact mode
+    float *vals;     // [B, heap_size] node values of numpy's pairwise tree, heap-indexed
+    int *rowcnt;     // [B] number of particles equal to the row maximum
+    unsigned long long *slots; // [B, nspans] (ready << 32 | carry bits) of each span of the chained scan
+    int *ticket;
+    int nspans, heap_depth, heap_size; // heap_depth: depth of the deepest leaf; heap_size = 2 << heap_depth
 };
 
 // ---- L1 ---------------------------------------------------------------------------------------------
@@ -146,57 +159,114 @@ __global__ void __launch_bounds__(kTileThreads) large_scan_kernel(const LargePar
     for (int k = tid; k < n; k += kTileThreads) p.W[off + k0 + k] = before + (s_pre[k / seg] + s_tile[k]);
 }
 
-// ---- L2 EXACT: scipy.special.logsumexp in numpy's summation order, one CTA per row ---------------------
-// numpy pairwise sum of e_i = (lw_i == vmax) ? 0 : np_exp(lw_i - vmax) over n consecutive particles
-__device__ float pairwise_exp_rec(const float *lw, int n, float vmax)
+// ---- L2 EXACT: scipy.special.logsumexp in numpy's summation order --------------------------------------
+// numpy's pairwise tree over K particles depends on K only.  A node is named by its heap index (root 1,
+// children 2h and 2h+1) and its extent is recomputed by walking the <= ~14 splits from the root, so no
+// tree is ever stored: leaves hold 64..128 particles, hence each contains a multiple of 64 and the leaf
+// kernel assigns one 8-lane group per such probe position (the first probe inside a leaf owns it).
+__device__ __forceinline__ int pw_left(int len)
 {
-    auto e = [&](int i) {
-        const float d = __fsub_rn(lw[i], vmax);
-        return (d == 0.0f) ? 0.0f : np_expf_nonpos(d);
-    };
-    if (n < 8) {
-        float r = 0.f;
-        for (int i = 0; i < n; ++i) r = __fadd_rn(r, e(i));
-        return r;
+    const int n2 = len >> 1;
+    return n2 - (n2 & 7);
+}
+__device__ __forceinline__ void pw_leaf_of(int K, int pos, int &start, int &len, int &heap)
+{
+    start = 0; len = K; heap = 1;
+    while (len > 128) {
+        const int n2 = pw_left(len);
+        if (pos < start + n2) { len = n2; heap = 2 * heap; }
+        else { start += n2; len -= n2; heap = 2 * heap + 1; }
     }
-    if (n <= 128) {
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = e(j);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], e(i + j));
-        }
-        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __fadd_rn(res, e(i));
-        return res;
+}
+// length of heap node h, 0 if the tree has no such node
+__device__ __forceinline__ int pw_node_len(int K, int h)
+{
+    int len = K;
+    for (int b = 30 - __clz(h); b >= 0; --b) {
+        if (len <= 128) return 0;
+        const int n2 = pw_left(len);
+        len = ((h >> b) & 1) ? len - n2 : n2;
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __fadd_rn(pairwise_exp_rec(lw, n2, vmax), pairwise_exp_rec(lw + n2, n - n2, vmax));
+    return len;
 }
 
-constexpr int kMacroLeaf = 1024;
+// (a) leaves: e_i = (lw_i == max) ? 0 : np_exp(lw_i - max), 8 strided accumulators per leaf (8 lanes).
+// A warp takes 32 consecutive probes: every lane walks to its probe's leaf, the owners are compacted
+// with a ballot, and the four 8-lane groups evaluate them four at a time.
+constexpr int kLeafThreads = 256;
 
-__global__ void __launch_bounds__(1024) large_exact_lse_kernel(const LargeParams p, int max_nodes)
+__global__ void __launch_bounds__(kLeafThreads) large_leaf_kernel(const LargeParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PwNode *nodes = reinterpret_cast<PwNode *>(smem_raw);
     __shared__ float s_f[32];
-    __shared__ int s_i[32];
-    __shared__ int s_lvl[kPairwiseMaxLevels + 1];
-    __shared__ int s_nlevels;
-    const int row = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-    const float *lw = p.log_w + (size_t)row * p.K;
+    const int row = blockIdx.y, tid = threadIdx.x, lane = tid & 31, K = p.K;
+    const float *lw = p.log_w + (size_t)row * K;
     const float vmax = row_max_from_tiles(p, row, s_f);
-    if (tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         p.rowmax[row] = vmax;
         if (!(fabsf(vmax) < INFINITY) && !p.rowbad[row]) { atomicOr(p.flags, AESMC_FLAG_DEGENERATE); atomicOr(p.rowbad + row, 2); }
-        build_pairwise_tree(nodes, s_lvl, &s_nlevels, p.K, kMacroLeaf);
     }
-    __syncthreads();
+    if (!(fabsf(vmax) < INFINITY)) return; // degenerate row: the fold kernel writes its lse
+    float *vals = p.vals + (size_t)row * p.heap_size;
+    const int pos = (blockIdx.x * kLeafThreads + tid) * 64;
+    int start = 0, len = 0, heap = 0;
+    bool owner = false;
+    if (pos < K) {
+        pw_leaf_of(K, pos, start, len, heap);
+        owner = (pos - 64 < start); // the first probe inside the leaf
+    }
+    const unsigned owners = __ballot_sync(kFull, owner);
+    const int nown = __popc(owners), grp = lane >> 3, j = lane & 7;
+    int cnt = 0;
+    auto e1 = [&](float v) {
+        const float d = __fsub_rn(v, vmax);
+        cnt += (d == 0.0f);
+        return (d == 0.0f) ? 0.0f : np_expf_nonpos(d);
+    };
+    auto e2 = [&](float v0, float v1, float &r0, float &r1) {
+        const float d0 = __fsub_rn(v0, vmax), d1 = __fsub_rn(v1, vmax);
+        np_expf_nonpos_pair(d0, d1, r0, r1);
+        cnt += (d0 == 0.0f) + (d1 == 0.0f);
+        if (d0 == 0.0f) r0 = 0.0f;
+        if (d1 == 0.0f) r1 = 0.0f;
+    };
+    for (int r = 0; r * 4 < nown; ++r) { // warp-uniform
+        const int which = r * 4 + grp;
+        const bool valid = which < nown;
+        const int src_lane = valid ? (int)__fns(owners, 0, which + 1) : 0;
+        const int g_start = __shfl_sync(kFull, start, src_lane), g_len = __shfl_sync(kFull, len, src_lane);
+        const int g_heap = __shfl_sync(kFull, heap, src_lane);
+        float acc = 0.f;
+        const int lim = g_len - (g_len & 7);
+        if (valid) { // 64 <= g_len <= 128
+            const float *src = lw + g_start + j;
+            acc = e1(src[0]);
+            int i = 8;
+            for (; i + 24 < lim; i += 32) { // four loads in flight per lane, exps two at a time
+                const float v0 = src[i], v1 = src[i + 8], v2 = src[i + 16], v3 = src[i + 24];
+                float r0, r1, r2, r3;
+                e2(v0, v1, r0, r1);
+                e2(v2, v3, r2, r3);
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, r0), r1), r2), r3);
+            }
+            for (; i < lim; i += 8) acc = __fadd_rn(acc, e1(src[i]));
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, 4));
+        if (valid && j == 0) {
+            for (int i = lim; i < g_len; ++i) acc = __fadd_rn(acc, e1(lw[g_start + i]));
+            vals[g_heap] = acc;
+        }
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0 && cnt) atomicAdd(p.rowcnt + row, cnt);
+}
+
+// (b) fold the levels bottom-up, finish the lse, one CTA per row
+__global__ void __launch_bounds__(1024) large_fold_kernel(const LargeParams p)
+{
+    const int row = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const float vmax = p.rowmax[row];
     if (p.rowbad[row]) {
         if (tid == 0) {
             const float lse = (p.rowbad[row] & 1) ? __int_as_float(0x7fc00000) : vmax;
@@ -205,23 +275,15 @@ __global__ void __launch_bounds__(1024) large_exact_lse_kernel(const LargeParams
         }
         return;
     }
-    int cnt = 0;
-    for (int k = tid; k < p.K; k += NT) cnt += (lw[k] == vmax);
-    cnt = block_allreduce(cnt, 0, OpSumI(), s_i);
-    const int nlevels = s_nlevels, nnodes = s_lvl[nlevels];
-    for (int n = tid; n < nnodes; n += NT)
-        if (nodes[n].child < 0) nodes[n].val = pairwise_exp_rec(lw + nodes[n].start, nodes[n].len, vmax);
-    __syncthreads();
-    for (int L = nlevels - 2; L >= 0; --L) {
-        for (int n = s_lvl[L] + tid; n < s_lvl[L + 1]; n += NT) {
-            const int ch = nodes[n].child;
-            if (ch >= 0) nodes[n].val = __fadd_rn(nodes[ch].val, nodes[ch + 1].val);
-        }
+    float *vals = p.vals + (size_t)row * p.heap_size;
+    for (int d = p.heap_depth - 1; d >= 0; --d) {
+        for (int h = (1 << d) + tid; h < (2 << d); h += NT)
+            if (pw_node_len(p.K, h) > 128) vals[h] = __fadd_rn(vals[2 * h], vals[2 * h + 1]);
         __syncthreads();
     }
     if (tid == 0) {
-        float s = nodes[0].val;
-        const float m = (float)cnt;
+        float s = vals[1];
+        const float m = (float)p.rowcnt[row];
         if (s != 0.0f) s = __fdiv_rn(s, m);
         const float lse = __fadd_rn(__fadd_rn(fd_log1pf(s), np_logf(m)), vmax);
         p.rowlse[row] = lse;
@@ -229,41 +291,126 @@ __global__ void __launch_bounds__(1024) large_exact_lse_kernel(const LargeParams
     }
 }
 
-// ---- L3 EXACT: np.cumsum's sequential chain, streamed with the exact carry ----------------------------
-__global__ void __launch_bounds__(1024) large_exact_scan_kernel(const LargeParams p)
+// ---- L3 EXACT: np.cumsum's sequential chain, spans chained across CTAs --------------------------------
+constexpr int kSpanThreads = 1024;
+constexpr int kSpan = kSpanThreads * kScanItems; // 16 384 particles = 4 tiles
+
+// (a) per-tile sums of the (approximate) normalised weights: the estimate of each span's entry value
+__global__ void __launch_bounds__(kTileThreads) large_wsum_kernel(const LargeParams p)
+{
+    __shared__ float s_f[32];
+    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    if (p.rowbad[row]) return;
+    const size_t off = (size_t)row * p.K;
+    const int k0 = tile * kTile, k1 = min(k0 + kTile, p.K);
+    const float shift = p.rowlse[row] * 1.4426950408889634f;
+    float part = 0.f;
+    for (int k = k0 + tid; k < k1; k += kTileThreads) part += exp2f(fmaf(p.log_w[off + k], 1.4426950408889634f, -shift));
+    part = block_allreduce(part, 0.f, OpSumF(), s_f);
+    if (tid == 0) p.tsum[(size_t)row * p.ntiles + tile] = part;
+}
+
+struct ChainedCarry {
+    static constexpr bool kChained = true;
+    float est, tol;
+    const unsigned long long *prev; // slot of the previous span, nullptr for the first
+    unsigned long long *mine;
+    __device__ __forceinline__ float anchor() const { return est; }
+    __device__ __forceinline__ float slack() const { return tol; }
+    __device__ __forceinline__ float wait() const
+    {
+        if (prev == nullptr) return 0.f;
+        unsigned long long v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(prev) : "memory");
+        } while ((v >> 32) == 0ull);
+        return __int_as_float((int)(unsigned)v);
+    }
+    __device__ __forceinline__ void publish(float s) const
+    {
+        const unsigned long long v = (1ull << 32) | (unsigned long long)(unsigned)__float_as_int(s);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mine), "l"(v) : "memory");
+    }
+};
+
+__global__ void __launch_bounds__(kSpanThreads) large_exact_scan_kernel(const LargeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x, NT = kSpanThreads;
     const int row_chunks = NT * 4 + (NT * 4 >> 3);
     float4 *bufW4 = reinterpret_cast<float4 *>(smem_raw);
     int *scratch = reinterpret_cast<int *>(bufW4 + row_chunks);
     float *bufW = reinterpret_cast<float *>(bufW4);
     __shared__ ExactScanShared s_scan;
+    __shared__ double s_d[32];
     __shared__ float s_carry;
-    const int row = blockIdx.x;
+    __shared__ int s_ticket;
+    // span-major tickets: whoever holds ticket t waits only for ticket t - B, which is already running
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int span = s_ticket / p.B, row = s_ticket - span * p.B;
     if (p.rowbad[row]) return;
     const size_t off = (size_t)row * p.K;
     const float lse = p.rowlse[row];
-    const int span = NT * kScanItems;
-    float carry = 0.f;
-    for (int base = 0; base < p.K; base += span) {
-        // normalised weights of this span into the padded buffer (striped, coalesced), zeros past K
-        for (int e = tid; e < span; e += NT) {
+    const int base = span * kSpan;
+
+    // estimate of the chain at the span start and its tolerance: the chain drifts from the real sum by
+    // ~sqrt(k) half-ulps on generic data (the bound k * 2^-24 is not used: a miss is detected and costs
+    // one redo of this span with the exact carry, never a wrong result)
+    double part = 0.0;
+    const int tiles_before = min(span * (kSpan / kTile), p.ntiles);
+    for (int t = tid; t < tiles_before; t += NT) part += (double)p.tsum[(size_t)row * p.ntiles + t];
+    part = block_allreduce(part, 0.0, OpSumD(), s_d);
+    ChainedCarry cc;
+    cc.est = (float)part;
+    cc.tol = cc.est * 5.9604644775390625e-08f * (32.0f * sqrtf((float)base) + 256.0f);
+    unsigned long long *slots = p.slots + (size_t)row * p.nspans;
+    cc.prev = span ? slots + span - 1 : nullptr;
+    cc.mine = slots + span;
+
+    // normalised weights of this span into the padded buffer (striped, coalesced), zeros past K
+    if ((p.K & 3) == 0) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = base + 4 * (tid + NT * i);
+            v[i] = (k < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.log_w + off + k))
+                             : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 r;
+            np_expf_nonpos_pair(__fsub_rn(v[i].x, lse), __fsub_rn(v[i].y, lse), r.x, r.y);
+            np_expf_nonpos_pair(__fsub_rn(v[i].z, lse), __fsub_rn(v[i].w, lse), r.z, r.w);
+            if (base + 4 * (tid + NT * i) >= p.K) r = make_float4(0.f, 0.f, 0.f, 0.f);
+            bufW4[pad_chunk(tid + NT * i)] = r;
+        }
+    } else {
+        for (int e = tid; e < kSpan; e += NT) {
             const int k = base + e;
             bufW[pad_elem(e)] = (k < p.K) ? np_expf_nonpos(__fsub_rn(p.log_w[off + k], lse)) : 0.0f;
         }
-        __syncthreads();
-        float w[kScanItems];
+    }
+    __syncthreads();
+    float w[kScanItems];
+    auto load_block = [&]() {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 v = bufW4[pad_chunk(4 * tid + i)];
             w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
-        float total;
-        if (!exact_cumsum_blocked(w, &total, bufW4, scratch, s_scan, carry)) {
+    };
+    load_block();
+    float total;
+    if (!exact_cumsum_blocked(w, &total, bufW4, scratch, s_scan, cc)) {
+        const bool published = (s_scan.fail == 0); // the walker succeeded, a replay check did not
+        const float carry = s_scan.carry_in;
+        __syncthreads();
+        load_block();
+        if (!exact_cumsum_blocked(w, &total, bufW4, scratch, s_scan, LocalCarry{carry})) {
             if (tid == 0) { // plain sequential chain over the span
                 float acc = carry;
-                for (int e = 0; e < span; ++e) { acc = __fadd_rn(acc, bufW[pad_elem(e)]); bufW[pad_elem(e)] = acc; }
+                for (int e = 0; e < kSpan; ++e) { acc = __fadd_rn(acc, bufW[pad_elem(e)]); bufW[pad_elem(e)] = acc; }
                 s_carry = acc;
             }
             __syncthreads();
@@ -271,18 +418,23 @@ __global__ void __launch_bounds__(1024) large_exact_scan_kernel(const LargeParam
 #pragma unroll
             for (int j = 0; j < kScanItems; ++j) w[j] = bufW[pad_elem(kScanItems * tid + j)];
         }
-        carry = total;
-#pragma unroll
-        for (int j = 0; j < kScanItems; ++j) {
-            const int k = base + kScanItems * tid + j;
-            if (k < p.K) p.W[off + k] = w[j];
-        }
-        __syncthreads();
+        if (!published && tid == 0) cc.publish(total);
     }
-    if (tid == 0) p.rowtotal[row] = carry;
+    const int kb = base + kScanItems * tid;
+    if ((p.K & 3) == 0 && kb + kScanItems <= p.K) {
+        float4 *dst = reinterpret_cast<float4 *>(p.W + off + kb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j)
+            if (kb + j < p.K) p.W[off + kb + j] = w[j];
+    }
+    if (span == p.nspans - 1 && tid == 0) p.rowtotal[row] = total;
 }
 
 // ---- L4: closed-form boundaries and run marks ---------------------------------------------------------
+// 16 consecutive particles per thread: the boundary of the predecessor is carried in a register
 __global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeParams p, int exact)
 {
     const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -290,25 +442,43 @@ __global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeP
     const size_t off = (size_t)row * p.K;
     const int K = p.K;
     const float total = p.rowtotal[row];
+    const float rcp = refined_rcp(total);
+    const bool safe_total = total > 9.3132257e-10f && total < 2.0f;
     const double u = p.u[row];
     const float u32 = (float)u, Kf = (float)K;
     const double Kd = (double)K, band = Kd * 8.8817841970012523e-16;
-    const bool filtered = K < (1 << 20);
-    const int k0 = tile * kTile, k1 = min(k0 + kTile, K);
-    for (int j = k0 + tid; j < k1; j += kTileThreads) {
-        // boundaries of particle j and of its predecessor (recomputed: avoids a cross-tile exchange)
-        int c[2];
+    // the float32 pre-filter sends 2 * tol32 of the particles to float64 anyway: past ~1 % nearly every
+    // warp runs both forms, so large rows use the float64 form alone
+    const bool filtered = K <= 65536;
+    constexpr int kPer = kTile / kTileThreads;
+    const int j0 = tile * kTile + kPer * tid;
+    if (j0 >= K) return;
+    float cdf[kPer];
+    if ((K & 3) == 0) { // j0 + kPer <= K or the tail chunks are past the row
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int jj = j - 1 + q;
-            if (jj < 0) { c[q] = 0; continue; }
-            const float cdf = p.W[off + jj];
-            const float cdfn = exact ? __fdiv_rn(cdf, total) : cdf / total;
-            c[q] = filtered ? count_positions_below_filtered(cdfn, u, u32, K, Kf, p.tol32)
-                            : count_positions_below(cdfn, u, K, Kd, band);
-            if (jj == K - 1) c[q] = K;
+        for (int i = 0; i < kPer / 4; ++i) {
+            const float4 v = (j0 + 4 * i < K) ? __ldg(reinterpret_cast<const float4 *>(p.W + off + j0) + i)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            cdf[4 * i] = v.x; cdf[4 * i + 1] = v.y; cdf[4 * i + 2] = v.z; cdf[4 * i + 3] = v.w;
         }
-        if (c[1] > c[0]) atomicMax(p.marks + off + c[0], j);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) cdf[i] = (j0 + i < K) ? p.W[off + j0 + i] : 0.f;
+    }
+    auto boundary = [&](float c) {
+        const float cdfn = exact ? div_hoisted(c, total, rcp, safe_total) : __fmul_rn(c, rcp);
+        return filtered ? count_positions_below_filtered(cdfn, u, u32, K, Kf, p.tol32)
+                        : count_positions_below(cdfn, u, K, Kd, band);
+    };
+    int c_prev = j0 ? boundary(p.W[off + j0 - 1]) : 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int j = j0 + i;
+        if (j < K) {
+            const int c = (j == K - 1) ? K : boundary(cdf[i]);
+            if (c > c_prev) atomicMax(p.marks + off + c_prev, j);
+            c_prev = c;
+        }
     }
 }
 
@@ -316,9 +486,9 @@ __global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeP
 __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeParams p, int exact)
 {
     __shared__ int s_tile[kTile];
-    __shared__ int s_wtot[32], s_pre[32];
-    __shared__ int s_enter;
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, nwarp = kTileThreads >> 5;
+    __shared__ int s_w[32];
+    constexpr int kPer = kTile / kTileThreads;
+    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)row * p.K;
     const int K = p.K, k0 = tile * kTile, n = min(kTile, K - k0);
     if (p.rowbad[row]) { // identity ancestry keeps downstream gathers in range
@@ -329,52 +499,104 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
         }
         return;
     }
-    if (tid == 0) {
-        // ancestor of the position just before the tile: #{j : cdf_j / total <= pos}, float64 compare
-        int enter = 0;
-        if (k0 > 0) {
-            const float total = p.rowtotal[row];
-            const double pos = __ddiv_rn(__dadd_rn(p.u[row], (double)(k0 - 1)), (double)K);
-            int lo = 0, hi = K;
-            while (lo < hi) {
-                const int mid = lo + ((hi - lo) >> 1);
-                const float cdf = p.W[off + mid];
-                const float cdfn = exact ? __fdiv_rn(cdf, total) : cdf / total;
-                if ((double)cdfn <= pos && mid != K - 1) lo = mid + 1; else hi = mid;
+    // ancestor of the position just before the tile: #{j : cdf_j / total <= pos}, float64 compare; the
+    // predicate is monotone in j, so the CTA narrows [lo, hi] 256-fold per round
+    int enter = 0;
+    if (k0 > 0) {
+        const float total = p.rowtotal[row];
+        const float rcp = refined_rcp(total);
+        const double pos = __ddiv_rn(__dadd_rn(p.u[row], (double)(k0 - 1)), (double)K);
+        int lo = 0, hi = K;
+        while (lo < hi) {
+            const int chunk = (hi - lo + kTileThreads - 1) / kTileThreads, first = lo + tid * chunk;
+            bool pred = false;
+            if (first < hi) {
+                const int j = min(first + chunk, hi) - 1;
+                const float cdf = p.W[off + j];
+                const float cdfn = exact ? __fdiv_rn(cdf, total) : __fmul_rn(cdf, rcp);
+                pred = ((double)cdfn <= pos) && (j != K - 1);
             }
-            enter = min(lo, K - 1);
+            const int ntrue = __syncthreads_count(pred);
+            const int nl = min(lo + ntrue * chunk, hi);
+            if (nl >= hi) lo = hi;
+            else { hi = min(nl + chunk, hi) - 1; lo = nl; }
         }
-        s_enter = enter;
+        enter = min(lo, K - 1);
     }
-    for (int k = tid; k < n; k += kTileThreads) s_tile[k] = p.marks[off + k0 + k];
-    __syncthreads();
-    const int seg = ((n + nwarp * 32 - 1) / (nwarp * 32)) * 32;
-    segment_scan_inplace(s_tile, n, seg, 0, OpMaxI(), s_wtot);
-    __syncthreads();
-    {
-        int run = s_enter;
-        for (int w = 0; w < nwarp; ++w) { const int t = s_wtot[w]; if (w == (tid >> 5)) s_pre[w] = run; run = max(run, t); }
-    }
-    __syncthreads();
-    for (int k = tid; k < n; k += kTileThreads) {
-        const int id = max(s_tile[k], s_pre[k / seg]);
-        s_tile[k] = id;
-        p.idx[off + k0 + k] = id;
-    }
-    if (p.x_in) {
-        __syncthreads();
-        const int D = p.D;
-        const float *xin = p.x_in + off * D;
-        float *xout = p.x_out + (off + k0) * D;
-        for (int e = tid; e < n * D; e += kTileThreads) {
-            const int k = e / D;
-            xout[e] = __ldg(xin + (size_t)s_tile[k] * D + (e - k * D));
+    // 16 consecutive positions per thread: running max of the marks, then across threads
+    const int kb = k0 + kPer * tid;
+    int m[kPer];
+    const bool vec = (K & 3) == 0;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i) {
+            const int4 v = (kb + 4 * i < K) ? __ldg(reinterpret_cast<const int4 *>(p.marks + off + kb) + i) : make_int4(0, 0, 0, 0);
+            m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) m[i] = (kb + i < K) ? p.marks[off + kb + i] : 0;
+    }
+#pragma unroll
+    for (int i = 1; i < kPer; ++i) m[i] = max(m[i], m[i - 1]);
+    int incl = m[kPer - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl = max(incl, v);
+    }
+    int pre = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) pre = 0;
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    pre = max(pre, enter);
+    for (int v = 0; v < warp; ++v) pre = max(pre, s_w[v]);
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) m[i] = max(m[i], pre);
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i)
+            if (kb + 4 * i < K)
+                reinterpret_cast<int4 *>(p.idx + off + kb)[i] = make_int4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i)
+            if (kb + i < K) p.idx[off + kb + i] = m[i];
+    }
+    if (!p.x_in) return;
+    if (p.D == 1 && vec) {
+        const float *xin = p.x_in + off;
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i)
+            if (kb + 4 * i < K)
+                reinterpret_cast<float4 *>(p.x_out + off + kb)[i] =
+                    make_float4(__ldg(xin + m[4 * i]), __ldg(xin + m[4 * i + 1]), __ldg(xin + m[4 * i + 2]), __ldg(xin + m[4 * i + 3]));
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) s_tile[kPer * tid + i] = m[i];
+    __syncthreads();
+    const int D = p.D;
+    const float *xin = p.x_in + off * D;
+    float *xout = p.x_out + (off + k0) * D;
+    for (int e = tid; e < n * D; e += kTileThreads) {
+        const int k = e / D;
+        xout[e] = __ldg(xin + (size_t)s_tile[k] * D + (e - k * D));
     }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// depth of the deepest leaf of numpy's pairwise tree over n elements (host; a few dozen distinct sizes)
+static int pairwise_depth(int n)
+{
+    if (n <= 128) return 0;
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const int l = pairwise_depth(n2);
+    return 1 + (n - n2 == n2 ? l : std::max(l, pairwise_depth(n - n2)));
+}
 
 int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K)
 {
@@ -383,6 +605,9 @@ int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K)
     bytes += align_up((size_t)B * K * 4) * 2;      // W, marks
     bytes += align_up((size_t)B * nt * 4) * 2;     // tmax, tsum
     bytes += align_up((size_t)B * 4) * 4;          // rowmax, rowtotal, rowlse, rowbad
+    const size_t nspans = (size_t)((K + kSpan - 1) / kSpan);
+    bytes += align_up((size_t)B * ((size_t)2 << pairwise_depth((int)K)) * 4); // heap of node values
+    bytes += align_up((size_t)B * 4 + (size_t)B * nspans * 8 + 8); // rowcnt, ticket, carry slots (one memset)
     return (int64_t)bytes;
 }
 
@@ -409,27 +634,39 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.rowmax = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowtotal = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowlse = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
-    p.rowbad = reinterpret_cast<int *>(ws);
+    p.rowbad = reinterpret_cast<int *>(ws); ws += align_up((size_t)B * 4);
+    p.nspans = (int)((K + kSpan - 1) / kSpan);
+    p.heap_depth = pairwise_depth((int)K);
+    p.heap_size = 2 << p.heap_depth;
+    p.vals = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.heap_size * 4);
+    const size_t zero_bytes = (size_t)B * 4 + (size_t)B * p.nspans * 8 + 8;
+    p.slots = reinterpret_cast<unsigned long long *>(ws);
+    p.ticket = reinterpret_cast<int *>(ws + (size_t)B * p.nspans * 8);
+    p.rowcnt = p.ticket + 2;
     cudaError_t e = cudaMemsetAsync(p.rowbad, 0, (size_t)B * 4, stream);
+    if (e == cudaSuccess && exact) e = cudaMemsetAsync(p.slots, 0, zero_bytes, stream);
     if (e == cudaSuccess && idx) e = cudaMemsetAsync(p.marks, 0, (size_t)B * K * 4, stream);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     const dim3 grid((unsigned)p.ntiles, (unsigned)B);
     large_prep_kernel<<<grid, kTileThreads, 0, stream>>>(p);
     count_launch();
-    if (exact && idx) {
-        const int max_nodes = pairwise_max_nodes((int)K); // generous: macro-leaves are 8x larger than leaves
-        const size_t smem_lse = (size_t)(2 * (K / 448 + 2)) * sizeof(PwNode); // macro-leaves hold >= 505 particles
-        e = cudaFuncSetAttribute(large_exact_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lse);
-        if (e != cudaSuccess) { set_error("K=%lld too large for the exact multi-CTA path: %s", (long long)K, cudaGetErrorString(e)); return AESMC_ERR_UNSUPPORTED; }
-        large_exact_lse_kernel<<<(unsigned)B, 1024, smem_lse, stream>>>(p, max_nodes);
+    if (exact) {
+        const int nprobes = (int)((K + 63) / 64);
+        const dim3 lgrid((unsigned)((nprobes + kLeafThreads - 1) / kLeafThreads), (unsigned)B);
+        large_leaf_kernel<<<lgrid, kLeafThreads, 0, stream>>>(p);
         count_launch();
-        const int nt = 1024;
-        const size_t row_chunks = (size_t)nt * 4 + ((size_t)nt * 4 >> 3);
-        const size_t smem_scan = row_chunks * 16 + (size_t)(8 * nt + 8) * 4;
-        e = cudaFuncSetAttribute(large_exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
-        large_exact_scan_kernel<<<(unsigned)B, nt, smem_scan, stream>>>(p);
+        large_fold_kernel<<<(unsigned)B, 1024, 0, stream>>>(p);
         count_launch();
+        if (idx) {
+            large_wsum_kernel<<<grid, kTileThreads, 0, stream>>>(p);
+            count_launch();
+            const size_t row_chunks = (size_t)kSpanThreads * 4 + ((size_t)kSpanThreads * 4 >> 3);
+            const size_t smem_scan = row_chunks * 16 + (size_t)(8 * kSpanThreads + 8) * 4;
+            e = cudaFuncSetAttribute(large_exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
+            large_exact_scan_kernel<<<(unsigned)(B * p.nspans), kSpanThreads, smem_scan, stream>>>(p);
+            count_launch();
+        }
     } else {
         large_expsum_kernel<<<grid, kTileThreads, 0, stream>>>(p);
         count_launch();

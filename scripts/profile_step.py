@@ -29,10 +29,12 @@ log_w = torch.empty(B, K, device=dev)
 lse = torch.empty(B, device=dev)
 idx = torch.empty(B, K, dtype=torch.int32, device=dev)
 flags = _ops.new_flags(dev)
+ws_bytes = int(_lib.load().aesmc_smc_step_workspace_bytes(B, K))  # > 0: rows larger than one CTA
+ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
 for i in range(args.launches):
     a, b, c = sets[i & 1]
-    _lib.call("aesmc_smc_step_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), u.data_ptr(), B, K, log_w.data_ptr(),
-              lse.data_ptr(), idx.data_ptr(), x[i & 1].data_ptr(), x[(i + 1) & 1].data_ptr(), D, flags.data_ptr(),
-              _ops.mode_code(args.mode))
+    _lib.call("aesmc_smc_step_ws_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), u.data_ptr(), B, K,
+              log_w.data_ptr(), lse.data_ptr(), idx.data_ptr(), x[i & 1].data_ptr(), x[(i + 1) & 1].data_ptr(), D,
+              flags.data_ptr(), _ops.mode_code(args.mode), ws.data_ptr() if ws_bytes else None, ws_bytes)
 torch.cuda.synchronize()
 print("flags", int(flags.item()))

@@ -291,6 +291,36 @@ def test_multi_cta_path_vs_oracle(cuda, B, K, D):
     np.testing.assert_allclose(lse3.cpu().numpy(), oracle.lse_f64(lw_ref), rtol=2e-6)
 
 
+@pytest.mark.parametrize("K", [50000, 300000])
+def test_multi_cta_exact_chain_stress(cuda, K):
+    """The span-chained exact cumulative sum (smc_step_large.cu): generic rows ride the speculative
+    estimate of each span's entry value; equal, sorted and dyadic weights drift systematically away from
+    it and take the redo-with-exact-carry path; sparse and dominated rows put whole spans below one ulp."""
+    rng = np.random.default_rng(K)
+    rows = [rng.standard_normal(K) - 1.4,
+            rng.standard_normal(K) * 6,
+            np.sort(rng.standard_normal(K) * 3),
+            np.sort(rng.standard_normal(K) * 3)[::-1],
+            np.full(K, -0.5),
+            np.log(2.0) * rng.integers(-30, 0, K),
+            np.where(rng.random(K) < 0.9, -np.inf, rng.standard_normal(K)),
+            np.concatenate([np.full(K // 2, -40.0), rng.standard_normal(K - K // 2)]),
+            np.log(np.maximum(rng.integers(0, 4, K), 1e-30) + 0.0)]
+    r = rng.standard_normal(K) * 0.01 - 70.0
+    r[K // 3] = 0.0
+    rows.append(r)
+    lw = np.stack(rows).astype(np.float32)
+    lw = np.concatenate([lw, (rng.standard_normal((6, K)) * rng.uniform(0.2, 5, (6, 1))).astype(np.float32)])
+    B = lw.shape[0]
+    u = rng.random(B)
+    (_, lse, idx, _), fl = run_step(lw, u, cuda)
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+    assert fl == 0 and st == 0
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+    bad = np.nonzero((idx.cpu().numpy() != np.minimum(idx_ref, K - 1)).any(axis=1))[0]
+    assert bad.size == 0, "rows with index mismatches: %s" % bad[:10]
+
+
 def test_multi_cta_flags(cuda):
     K = 50000
     lw = np.zeros((3, K), np.float32)
