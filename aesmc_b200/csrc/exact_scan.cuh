@@ -70,7 +70,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
                                                      int *scratch, ExactScanShared &sh, const Carry carry)
 {
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed
+    int *recE = scratch;                 // biased exponent of a pure block's binade, 0 = mixed, -1 = all zero
     int *recG0 = scratch + NT;           // inclusive composed map of the run up to this block
     int *recG1 = scratch + 2 * NT;
     float *seg_state = reinterpret_cast<float *>(scratch + 3 * NT); // chain value at each segment start (NT+1)
@@ -108,11 +108,14 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         const int el = __float_as_int(lo) >> 23, eh = __float_as_int(hi) >> 23;
         if (el == eh) eb = el;
     }
+    // a block of zero weights (padding past K, -inf log-weights) is the identity map in every binade:
+    // eb = -1, so that the tail of a row, whose sum sits at the binade boundary 1.0, is not walked
+    if (ls == 0.f) eb = -1;
 
     // ---- pure block -> (c0, c1): the scaled chain from an even and an odd start -------------------
-    const float scale = __int_as_float((277 - (eb ? eb : 127)) << 23); // 2^(23 - e), exact multiplier
+    const float scale = __int_as_float((277 - (eb > 0 ? eb : 127)) << 23); // 2^(23 - e), exact multiplier
     int c0 = 0, c1 = 0;
-    if (eb) {
+    if (eb > 0) {
         // (m0, m1) = (2^23, 2^23 + 1): ulp 1, so RN == round-half-even to integer; both parities advance
         // in one packed FADD2 per particle
         f32x2 m01 = pack2(8388608.0f, 8388609.0f);
@@ -179,14 +182,14 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         for (int i = 0; i < nseg; ++i) {
             const int t = rec.x, e = rec.y, r0 = rec.z, r1 = rec.w;
             if (i + 1 < nseg) rec = seg_rec[i + 1]; // independent of the chain: overlaps with it
-            if (e) {
+            if (e > 0) {
                 const int sb = __float_as_int(s);
                 if ((sb >> 23) != e) { fail = 1; break; }
                 int m = (sb & 0x7fffff) | 0x800000;
                 m += (m & 1) ? r1 : r0;
                 if (m > 0x1000000) { fail = 1; break; }
                 s = (m == 0x1000000) ? __int_as_float((e + 1) << 23) : __int_as_float((e << 23) | (m & 0x7fffff));
-            } else {
+            } else if (e == 0) {
 #pragma unroll
                 for (int c = 0; c < kScanItems / 4; ++c) {
                     const float4 v = bufW4[pad_chunk(4 * t + c)];
@@ -204,7 +207,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     // ---- every thread replays its own block from its exact entry state ----------------------------
     int bad = sh.fail;
     const float s0 = seg_state[segidx];
-    if (eb) {
+    if (eb > 0) {
         const int sb = __float_as_int(s0);
         int m = (sb & 0x7fffff) | 0x800000;
         if ((sb >> 23) != eb) bad = 1;

@@ -29,6 +29,8 @@
 #include "scan.cuh"
 #include "exact_scan.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace aesmc {
 
@@ -58,7 +60,8 @@ struct LargeParams {
     float *vals;     // [B, heap_size] node values of numpy's pairwise tree, heap-indexed
     int *rowcnt;     // [B] number of particles equal to the row maximum
     unsigned long long *slots; // [B, nspans] (ready << 32 | carry bits) of each span of the chained scan
-    int *ticket;
+    int *ticket;     // [0] span tickets, [1] padding; then rowcnt
+    int *stats;      // [4] redo after a missed estimate / after a failed replay check / sequential spans
     int nspans, heap_depth, heap_size; // heap_depth: depth of the deepest leaf; heap_size = 2 << heap_depth
 };
 
@@ -292,8 +295,10 @@ __global__ void __launch_bounds__(1024) large_fold_kernel(const LargeParams p)
 }
 
 // ---- L3 EXACT: np.cumsum's sequential chain, spans chained across CTAs --------------------------------
-constexpr int kSpanThreads = 1024;
-constexpr int kSpan = kSpanThreads * kScanItems; // 16 384 particles = 4 tiles
+// Span = NT * 16 particles.  A hand-off costs ~0.5 us, so 1024-thread spans (one CTA per SM) keep the
+// carry chain of a row short and win while the launch is chain-bound (few rows); with many rows the
+// chains overlap and 512-thread spans (two CTAs per SM, one hiding the other's barriers) have the better
+// throughput.  Measured on B200, K = 1e6: B = 8: 71 vs 106 us; B = 64: 331 vs 256 us.
 
 // (a) per-tile sums of the (approximate) normalised weights: the estimate of each span's entry value
 __global__ void __launch_bounds__(kTileThreads) large_wsum_kernel(const LargeParams p)
@@ -333,10 +338,12 @@ struct ChainedCarry {
     }
 };
 
-__global__ void __launch_bounds__(kSpanThreads) large_exact_scan_kernel(const LargeParams p)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const LargeParams p)
 {
+    constexpr int kSpan = NT * kScanItems;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, NT = kSpanThreads;
+    const int tid = threadIdx.x;
     const int row_chunks = NT * 4 + (NT * 4 >> 3);
     float4 *bufW4 = reinterpret_cast<float4 *>(smem_raw);
     int *scratch = reinterpret_cast<int *>(bufW4 + row_chunks);
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(kSpanThreads) large_exact_scan_kernel(const La
     part = block_allreduce(part, 0.0, OpSumD(), s_d);
     ChainedCarry cc;
     cc.est = (float)part;
-    cc.tol = cc.est * 5.9604644775390625e-08f * (32.0f * sqrtf((float)base) + 256.0f);
+    cc.tol = cc.est * 5.9604644775390625e-08f * (8.0f * sqrtf((float)base) + 64.0f);
     unsigned long long *slots = p.slots + (size_t)row * p.nspans;
     cc.prev = span ? slots + span - 1 : nullptr;
     cc.mine = slots + span;
@@ -405,10 +412,12 @@ __global__ void __launch_bounds__(kSpanThreads) large_exact_scan_kernel(const La
     if (!exact_cumsum_blocked(w, &total, bufW4, scratch, s_scan, cc)) {
         const bool published = (s_scan.fail == 0); // the walker succeeded, a replay check did not
         const float carry = s_scan.carry_in;
+        if (tid == 0) atomicAdd(p.stats + (s_scan.fail == 2 ? 0 : 1), 1);
         __syncthreads();
         load_block();
         if (!exact_cumsum_blocked(w, &total, bufW4, scratch, s_scan, LocalCarry{carry})) {
             if (tid == 0) { // plain sequential chain over the span
+                atomicAdd(p.stats + 2, 1);
                 float acc = carry;
                 for (int e = 0; e < kSpan; ++e) { acc = __fadd_rn(acc, bufW[pad_elem(e)]); bufW[pad_elem(e)] = acc; }
                 s_carry = acc;
@@ -605,9 +614,9 @@ int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K)
     bytes += align_up((size_t)B * K * 4) * 2;      // W, marks
     bytes += align_up((size_t)B * nt * 4) * 2;     // tmax, tsum
     bytes += align_up((size_t)B * 4) * 4;          // rowmax, rowtotal, rowlse, rowbad
-    const size_t nspans = (size_t)((K + kSpan - 1) / kSpan);
+    const size_t nspans = (size_t)((K + 8191) / 8192); // room for the smallest span size
     bytes += align_up((size_t)B * ((size_t)2 << pairwise_depth((int)K)) * 4); // heap of node values
-    bytes += align_up((size_t)B * 4 + (size_t)B * nspans * 8 + 8); // rowcnt, ticket, carry slots (one memset)
+    bytes += align_up((size_t)B * 4 + (size_t)B * nspans * 8 + 8 + 16); // rowcnt, ticket, carry slots, stats (one memset)
     return (int64_t)bytes;
 }
 
@@ -635,14 +644,18 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.rowtotal = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowlse = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowbad = reinterpret_cast<int *>(ws); ws += align_up((size_t)B * 4);
-    p.nspans = (int)((K + kSpan - 1) / kSpan);
+    static const int span_env = getenv("AESMC_SPAN_THREADS") ? atoi(getenv("AESMC_SPAN_THREADS")) : 0;
+    int span_threads = (B >= 24) ? 512 : 1024;
+    if (span_env == 512 || span_env == 1024) span_threads = span_env;
+    p.nspans = (int)((K + span_threads * kScanItems - 1) / (span_threads * kScanItems));
     p.heap_depth = pairwise_depth((int)K);
     p.heap_size = 2 << p.heap_depth;
     p.vals = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.heap_size * 4);
-    const size_t zero_bytes = (size_t)B * 4 + (size_t)B * p.nspans * 8 + 8;
+    const size_t zero_bytes = (size_t)B * 4 + (size_t)B * p.nspans * 8 + 8 + 16;
     p.slots = reinterpret_cast<unsigned long long *>(ws);
     p.ticket = reinterpret_cast<int *>(ws + (size_t)B * p.nspans * 8);
-    p.rowcnt = p.ticket + 2;
+    p.stats = p.ticket + 2;
+    p.rowcnt = p.stats + 4;
     cudaError_t e = cudaMemsetAsync(p.rowbad, 0, (size_t)B * 4, stream);
     if (e == cudaSuccess && exact) e = cudaMemsetAsync(p.slots, 0, zero_bytes, stream);
     if (e == cudaSuccess && idx) e = cudaMemsetAsync(p.marks, 0, (size_t)B * K * 4, stream);
@@ -660,11 +673,16 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
         if (idx) {
             large_wsum_kernel<<<grid, kTileThreads, 0, stream>>>(p);
             count_launch();
-            const size_t row_chunks = (size_t)kSpanThreads * 4 + ((size_t)kSpanThreads * 4 >> 3);
-            const size_t smem_scan = row_chunks * 16 + (size_t)(8 * kSpanThreads + 8) * 4;
-            e = cudaFuncSetAttribute(large_exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan);
+            const size_t row_chunks = (size_t)span_threads * 4 + ((size_t)span_threads * 4 >> 3);
+            const size_t smem_scan = row_chunks * 16 + (size_t)(8 * span_threads + 8) * 4;
+            auto launch = [&](auto kernel) {
+                cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan);
+                if (err != cudaSuccess) return err;
+                kernel<<<(unsigned)(B * p.nspans), span_threads, smem_scan, stream>>>(p);
+                return cudaSuccess;
+            };
+            e = span_threads == 1024 ? launch(large_exact_scan_kernel<1024>) : launch(large_exact_scan_kernel<512>);
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
-            large_exact_scan_kernel<<<(unsigned)(B * p.nspans), kSpanThreads, smem_scan, stream>>>(p);
             count_launch();
         }
     } else {
@@ -678,6 +696,13 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
         count_launch();
         large_expand_kernel<<<grid, kTileThreads, 0, stream>>>(p, exact ? 1 : 0);
         count_launch();
+    }
+    if (exact && idx && getenv("AESMC_DEBUG_STATS")) { // debugging aid: synchronises
+        int h[4] = {0, 0, 0, 0};
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, p.stats, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[aesmc] chained scan: %d spans, redo after missed estimate %d, after replay check %d, sequential %d\n",
+                (int)(B * p.nspans), h[0], h[1], h[2]);
     }
     return check_launch("smc_step_large");
 }
