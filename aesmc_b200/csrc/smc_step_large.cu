@@ -5,24 +5,26 @@
 // a serial chain:
 //
 //   L1 prep      log_w = (a+b)-c -> HBM, per-tile max, NaN flag                      grid (tiles, B)
-//   L2 weights   FAST : e = exp2(lw - max) -> W, per-tile sums                       grid (tiles, B)
+//                FAST : also the tile-local running sums of exp2(lw - tile max) -> W
+//   L2 weights   FAST : per-tile scale and offset, row total, lse                    grid (B)
 //                EXACT: scipy/numpy-order lse.  numpy's pairwise-summation tree depends on K only and
 //                       is never stored (heap indices, extents recomputed from the root): its leaves
 //                       (64..128 particles, 8 lanes each) are evaluated by a (chunks, B) grid, one CTA
 //                       per row folds the levels.
-//   L3 cdf       FAST : tile scan + offset from the tile sums                        grid (tiles, B)
+//   L3 cdf       FAST : none -- consumers evaluate before_t + W_j * scale_t on the fly
 //                EXACT: the reference's sequential float32 cumulative sum.  The row is cut into spans
 //                       of 16 384 particles owned by different CTAs (dynamic tickets, span-major): each
 //                       classifies and composes its blocks against an estimate of its entry value while
 //                       its predecessor is still running, then waits for the exact carry, walks its
 //                       ~20 segments, publishes its exit value and only then replays (exact_scan.cuh).
-//   L4 search    closed-form offspring boundaries c_j, run starts scattered into      grid (tiles, B)
-//                a zeroed [B, K] int32 mark table (atomicMax)
-//   L5 expand    one float64 binary search per tile for the ancestor entering the     grid (tiles, B)
-//                tile, max-scan of the tile's marks, idx out, ancestral gather
+//   L4 search    closed-form offspring boundaries c_j; run starts scattered as marks  grid (tiles, B)
+//                into the zeroed idx output itself; the particle whose run covers the
+//                position just before a tile boundary is recorded as that tile's entry
+//   L5 expand    max-scan of the tile's marks from its entry ancestor, idx in place,  grid (tiles, B)
+//                ancestral gather
 //
-// Workspace (caller-allocated, aesmc_smc_step_workspace_bytes): W [B,K] f32, marks [B,K] i32, per-tile
-// max / sum [B, tiles], per-row max / total / lse, the heap of summation-tree node values of each row,
+// Workspace (caller-allocated, aesmc_smc_step_workspace_bytes): W [B,K] f32, per-tile max / sum / offset /
+// scale / entry [B, tiles], per-row max / total / lse, the heap of summation-tree node values of each row,
 // one 8-byte carry slot per span.
 #include "common.cuh"
 #include "pairwise.cuh"
@@ -48,7 +50,7 @@ struct LargeParams {
     int D;
     int32_t *flags;
     float *W;        // [B, K]
-    int *marks;      // [B, K]
+    int *marks;      // [B, K]: the idx output doubles as the table of run marks
     float *tmax;     // [B, ntiles]
     float *tsum;     // [B, ntiles]
     float *rowmax;   // [B]
@@ -56,6 +58,11 @@ struct LargeParams {
     float *rowlse;   // [B]
     int *rowbad;     // [B] 1: NaN, 2: degenerate
     float tol32;
+    // fast mode: W holds tile-local sums, cdf_j = before[t] + W_j * scale[t]
+    double *tbefore; // [B, ntiles + 1]
+    double *tscale;  // [B, ntiles]
+    int tiled;
+    int *tenter;     // [B, ntiles] ancestor of the position just before each tile (written by the search)
     // exact mode
     float *vals;     // [B, heap_size] node values of numpy's pairwise tree, heap-indexed
     int *rowcnt;     // [B] number of particles equal to the row maximum
@@ -66,27 +73,112 @@ struct LargeParams {
 };
 
 // ---- L1 ---------------------------------------------------------------------------------------------
+// FAST additionally leaves in W the tile-local inclusive sums L_j of e_j = exp2((lw_j - m_t) log2 e), m_t
+// the TILE maximum: the row-level quantities then follow from the per-tile (m_t, L_last) pairs alone
+// (large_rows_fast_kernel) and the CDF entry of particle j is before_t + L_j * scale_t, evaluated on the
+// fly by the search and expansion kernels -- no second and third pass over the row.
+template <bool FAST>
 __global__ void __launch_bounds__(kTileThreads) large_prep_kernel(const LargeParams p)
 {
     __shared__ float s_f[32];
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    __shared__ __align__(16) float s_e[FAST ? kTile + kTile / 8 : 4];
+    constexpr int kPer = kTile / kTileThreads;
+    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)row * p.K;
-    const int k0 = tile * kTile, k1 = min(k0 + kTile, p.K);
+    const int K = p.K, k0 = tile * kTile;
+    const bool vec = (K & 3) == 0;
+    float lw[kPer]; // vec: float4 chunks tid + 256 i; else elements tid + 256 i
     float vmax = -INFINITY;
     int bad = 0;
-    for (int k = k0 + tid; k < k1; k += kTileThreads) {
-        float v = p.a[off + k];
-        if (p.b) v = __fadd_rn(v, p.b[off + k]);
-        if (p.c) v = __fsub_rn(v, p.c[off + k]);
-        p.log_w[off + k] = v;
-        bad |= (v != v);
-        vmax = fmaxf(vmax, v);
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i) {
+            const int k = k0 + 4 * (tid + kTileThreads * i);
+            float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (k < K) {
+                v = __ldg(reinterpret_cast<const float4 *>(p.a + off + k));
+                if (p.b) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(p.b + off + k));
+                    v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w);
+                }
+                if (p.c) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(p.c + off + k));
+                    v.x = __fsub_rn(v.x, t.x); v.y = __fsub_rn(v.y, t.y); v.z = __fsub_rn(v.z, t.z); v.w = __fsub_rn(v.w, t.w);
+                }
+                *reinterpret_cast<float4 *>(p.log_w + off + k) = v;
+            }
+            lw[4 * i] = v.x; lw[4 * i + 1] = v.y; lw[4 * i + 2] = v.z; lw[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int k = k0 + tid + kTileThreads * i;
+            float v = -INFINITY;
+            if (k < K) {
+                v = p.a[off + k];
+                if (p.b) v = __fadd_rn(v, p.b[off + k]);
+                if (p.c) v = __fsub_rn(v, p.c[off + k]);
+                p.log_w[off + k] = v;
+            }
+            lw[i] = v;
+        }
     }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { bad |= (lw[i] != lw[i]); vmax = fmaxf(vmax, lw[i]); }
     vmax = block_allreduce(vmax, -INFINITY, OpMaxF(), s_f);
     bad = __syncthreads_or(bad);
     if (tid == 0) {
         p.tmax[(size_t)row * p.ntiles + tile] = vmax;
         if (bad) { atomicOr(p.flags, AESMC_FLAG_NAN); atomicOr(p.rowbad + row, 1); }
+    }
+    if (!FAST) return;
+    // e_j in the padded tile buffer, then 16 consecutive particles per thread
+    const float shift = (fabsf(vmax) < INFINITY ? vmax : 0.f) * 1.4426950408889634f;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i) {
+            float4 e;
+            e.x = exp2f(fmaf(lw[4 * i], 1.4426950408889634f, -shift)); e.y = exp2f(fmaf(lw[4 * i + 1], 1.4426950408889634f, -shift));
+            e.z = exp2f(fmaf(lw[4 * i + 2], 1.4426950408889634f, -shift)); e.w = exp2f(fmaf(lw[4 * i + 3], 1.4426950408889634f, -shift));
+            reinterpret_cast<float4 *>(s_e)[pad_chunk(tid + kTileThreads * i)] = e;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) s_e[pad_elem(tid + kTileThreads * i)] = exp2f(fmaf(lw[i], 1.4426950408889634f, -shift));
+    }
+    __syncthreads();
+    float w[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4 *>(s_e)[pad_chunk(4 * tid + i)];
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 1; i < kPer; ++i) w[i] += w[i - 1];
+    float incl = w[kPer - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_f[warp] = incl;
+    __syncthreads();
+    float pre = incl - w[kPer - 1];
+    for (int v = 0; v < warp; ++v) pre += s_f[v];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) w[i] += pre;
+    if (tid == kTileThreads - 1) p.tsum[(size_t)row * p.ntiles + tile] = w[kPer - 1]; // past K: e = 0, L stays flat
+    if (!p.idx) return;
+    const int kb = k0 + kPer * tid;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < kPer / 4; ++i)
+            if (kb + 4 * i < K)
+                reinterpret_cast<float4 *>(p.W + off + kb)[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i)
+            if (kb + i < K) p.W[off + kb + i] = w[i];
     }
 }
 
@@ -98,68 +190,62 @@ __device__ __forceinline__ float row_max_from_tiles(const LargeParams &p, int ro
     return block_allreduce(m, -INFINITY, OpMaxF(), s_f);
 }
 
-// ---- L2 FAST ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads) large_expsum_kernel(const LargeParams p)
+// ---- L2 FAST: row maximum, per-tile scale exp(m_t - M) and offset, row total, lse -- one CTA per row ----
+// before[t+1] = before[t] + L_last(t) * scale_t with explicitly rounded float64 operations, the same
+// expression the consumers evaluate for every particle (cdf_from_tile), so the CDF is monotone across
+// tile boundaries by construction.
+__device__ __forceinline__ float cdf_from_tile(float L, double before, double scale)
 {
-    __shared__ float s_f[32];
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const size_t off = (size_t)row * p.K;
-    const float vmax = row_max_from_tiles(p, row, s_f);
-    if (tile == 0 && tid == 0) {
-        p.rowmax[row] = vmax;
-        if (!(fabsf(vmax) < INFINITY) && !p.rowbad[row]) { atomicOr(p.flags, AESMC_FLAG_DEGENERATE); atomicOr(p.rowbad + row, 2); }
-    }
-    const int k0 = tile * kTile, k1 = min(k0 + kTile, p.K);
-    const float shift = vmax * 1.4426950408889634f;
-    float part = 0.f;
-    for (int k = k0 + tid; k < k1; k += kTileThreads) {
-        const float e = exp2f(fmaf(p.log_w[off + k], 1.4426950408889634f, -shift));
-        if (p.idx) p.W[off + k] = e;
-        part += e;
-    }
-    part = block_allreduce(part, 0.f, OpSumF(), s_f);
-    if (tid == 0) p.tsum[(size_t)row * p.ntiles + tile] = part;
+    return __double2float_rn(__dadd_rn(before, __dmul_rn((double)L, scale)));
 }
 
-// ---- L3 FAST ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads) large_scan_kernel(const LargeParams p)
+__global__ void __launch_bounds__(256) large_rows_fast_kernel(const LargeParams p)
 {
-    __shared__ float s_tile[kTile];
-    __shared__ float s_wtot[32], s_pre[32];
-    __shared__ double s_d[2];
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, nwarp = kTileThreads >> 5;
-    const size_t off = (size_t)row * p.K;
-    if (tid == 0) { // tile sums are folded in a fixed order, in double: offsets are monotone across tiles
-        double before = 0.0, all = 0.0;
-        for (int t = 0; t < p.ntiles; ++t) {
-            const double v = (double)p.tsum[(size_t)row * p.ntiles + t];
-            if (t == tile) before = all;
-            all += v;
-        }
-        s_d[0] = before;
-        s_d[1] = all;
-        if (tile == 0) {
-            const float lse = p.rowbad[row] ? ((p.rowbad[row] & 1) ? __int_as_float(0x7fc00000) : p.rowmax[row])
-                                             : p.rowmax[row] + (float)log(all);
+    __shared__ float s_f[32];
+    __shared__ double s_prod[1024];
+    __shared__ double s_carry;
+    const int row = blockIdx.x, tid = threadIdx.x, nt = p.ntiles;
+    const float vmax = row_max_from_tiles(p, row, s_f);
+    double *before = p.tbefore + (size_t)row * (nt + 1);
+    double *scale = p.tscale + (size_t)row * nt;
+    if (tid == 0) {
+        p.rowmax[row] = vmax;
+        if (!(fabsf(vmax) < INFINITY) && !p.rowbad[row]) { atomicOr(p.flags, AESMC_FLAG_DEGENERATE); p.rowbad[row] |= 2; }
+        s_carry = 0.0;
+    }
+    __syncthreads();
+    if (p.rowbad[row]) {
+        if (tid == 0) {
+            const float lse = (p.rowbad[row] & 1) ? __int_as_float(0x7fc00000) : vmax;
             p.rowlse[row] = lse;
-            p.rowtotal[row] = (float)all;
             if (p.lse) p.lse[row] = lse;
         }
+        return;
     }
-    if (!p.idx) return;
-    const int k0 = tile * kTile, n = min(kTile, p.K - k0);
-    for (int k = tid; k < n; k += kTileThreads) s_tile[k] = p.W[off + k0 + k];
-    __syncthreads();
-    const int seg = ((n + nwarp * 32 - 1) / (nwarp * 32)) * 32;
-    segment_scan_inplace(s_tile, n, seg, 0.f, OpSumF(), s_wtot);
-    __syncthreads();
-    {
-        float run = 0.f;
-        for (int w = 0; w < nwarp; ++w) { const float t = s_wtot[w]; if (w == (tid >> 5)) s_pre[w] = run; run += t; }
+    for (int base = 0; base < nt; base += 1024) {
+        const int cnt = min(1024, nt - base);
+        for (int t = tid; t < cnt; t += blockDim.x) {
+            const float mt = p.tmax[(size_t)row * nt + base + t];
+            const double sc = exp((double)mt - (double)vmax); // m_t = -inf: 0
+            scale[base + t] = sc;
+            s_prod[t] = __dmul_rn((double)p.tsum[(size_t)row * nt + base + t], sc);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double acc = s_carry;
+            for (int t = 0; t < cnt; ++t) { before[base + t] = acc; acc = __dadd_rn(acc, s_prod[t]); }
+            s_carry = acc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const float before = (float)s_d[0];
-    for (int k = tid; k < n; k += kTileThreads) p.W[off + k0 + k] = before + (s_pre[k / seg] + s_tile[k]);
+    if (tid == 0) {
+        const double all = s_carry;
+        before[nt] = all;
+        const float lse = vmax + (float)log(all);
+        p.rowlse[row] = lse;
+        p.rowtotal[row] = __double2float_rn(all);
+        if (p.lse) p.lse[row] = lse;
+    }
 }
 
 // ---- L2 EXACT: scipy.special.logsumexp in numpy's summation order --------------------------------------
@@ -444,12 +530,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
 
 // ---- L4: closed-form boundaries and run marks ---------------------------------------------------------
 // 16 consecutive particles per thread: the boundary of the predecessor is carried in a register
-__global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeParams p, int exact)
+template <bool EXACT, bool TILED>
+__global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeParams p)
 {
     const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     if (p.rowbad[row]) return;
-    const size_t off = (size_t)row * p.K;
     const int K = p.K;
+    constexpr int kPer = kTile / kTileThreads;
+    const int j0 = tile * kTile + kPer * tid;
+    if (j0 >= K) return;
+    const float *Wrow = p.W + (size_t)row * K;
+    int *marks = p.marks + (size_t)row * K;
+    int *tenter = p.tenter + (size_t)row * p.ntiles;
     const float total = p.rowtotal[row];
     const float rcp = refined_rcp(total);
     const bool safe_total = total > 9.3132257e-10f && total < 2.0f;
@@ -459,42 +551,51 @@ __global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeP
     // the float32 pre-filter sends 2 * tol32 of the particles to float64 anyway: past ~1 % nearly every
     // warp runs both forms, so large rows use the float64 form alone
     const bool filtered = K <= 65536;
-    constexpr int kPer = kTile / kTileThreads;
-    const int j0 = tile * kTile + kPer * tid;
-    if (j0 >= K) return;
+    const double t_before = TILED ? p.tbefore[(size_t)row * (p.ntiles + 1) + tile] : 0.0;
+    const double t_scale = TILED ? p.tscale[(size_t)row * p.ntiles + tile] : 0.0;
     float cdf[kPer];
     if ((K & 3) == 0) { // j0 + kPer <= K or the tail chunks are past the row
 #pragma unroll
         for (int i = 0; i < kPer / 4; ++i) {
-            const float4 v = (j0 + 4 * i < K) ? __ldg(reinterpret_cast<const float4 *>(p.W + off + j0) + i)
+            const float4 v = (j0 + 4 * i < K) ? __ldg(reinterpret_cast<const float4 *>(Wrow + j0) + i)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
             cdf[4 * i] = v.x; cdf[4 * i + 1] = v.y; cdf[4 * i + 2] = v.z; cdf[4 * i + 3] = v.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) cdf[i] = (j0 + i < K) ? p.W[off + j0 + i] : 0.f;
+        for (int i = 0; i < kPer; ++i) cdf[i] = (j0 + i < K) ? Wrow[j0 + i] : 0.f;
     }
     auto boundary = [&](float c) {
-        const float cdfn = exact ? div_hoisted(c, total, rcp, safe_total) : __fmul_rn(c, rcp);
+        if (TILED) c = cdf_from_tile(c, t_before, t_scale);
+        const float cdfn = EXACT ? div_hoisted(c, total, rcp, safe_total) : __fmul_rn(c, rcp);
         return filtered ? count_positions_below_filtered(cdfn, u, u32, K, Kf, p.tol32)
                         : count_positions_below(cdfn, u, K, Kd, band);
     };
-    int c_prev = j0 ? boundary(p.W[off + j0 - 1]) : 0;
+    // predecessor: in this tile, or the last particle of the previous one (whose CDF entry is before_t)
+    int c_prev = 0;
+    if (j0) c_prev = (TILED && tid == 0) ? boundary(0.f) : boundary(Wrow[j0 - 1]);
+    const int last_i = K - 1 - j0; // particle K-1 owns every remaining position; later slots are past the row
 #pragma unroll
     for (int i = 0; i < kPer; ++i) {
-        const int j = j0 + i;
-        if (j < K) {
-            const int c = (j == K - 1) ? K : boundary(cdf[i]);
-            if (c > c_prev) atomicMax(p.marks + off + c_prev, j);
-            c_prev = c;
+        int c = boundary(cdf[i]);
+        if (i >= last_i) c = K;
+        if (c > c_prev) {
+            atomicMax(marks + c_prev, j0 + i); // one writer per entry (c is monotone in j)
+            // a position 4096 T - 1 inside [c_prev, c): this particle is the ancestor entering tile T
+            if ((c >> 12) != (c_prev >> 12))
+                for (int t = (c_prev >> 12) + 1; t <= (c >> 12) && t < p.ntiles; ++t) tenter[t] = j0 + i;
         }
+        c_prev = c;
     }
 }
 
 // ---- L5: expansion of the run marks into ancestor indices, gather -------------------------------------
-__global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeParams p, int exact)
+// Global traffic is chunk-striped (thread t owns 16-byte chunks t + 256 i: fully coalesced, and the
+// gather of a warp stays within a few sectors because ancestors are sorted); the max-scan wants 16
+// consecutive positions per thread; the padded tile buffer converts between the two.
+__global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeParams p)
 {
-    __shared__ int s_tile[kTile];
+    __shared__ __align__(16) int s_tile[kTile + kTile / 8];
     __shared__ int s_w[32];
     constexpr int kPer = kTile / kTileThreads;
     const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -508,43 +609,29 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
         }
         return;
     }
-    // ancestor of the position just before the tile: #{j : cdf_j / total <= pos}, float64 compare; the
-    // predicate is monotone in j, so the CTA narrows [lo, hi] 256-fold per round
-    int enter = 0;
-    if (k0 > 0) {
-        const float total = p.rowtotal[row];
-        const float rcp = refined_rcp(total);
-        const double pos = __ddiv_rn(__dadd_rn(p.u[row], (double)(k0 - 1)), (double)K);
-        int lo = 0, hi = K;
-        while (lo < hi) {
-            const int chunk = (hi - lo + kTileThreads - 1) / kTileThreads, first = lo + tid * chunk;
-            bool pred = false;
-            if (first < hi) {
-                const int j = min(first + chunk, hi) - 1;
-                const float cdf = p.W[off + j];
-                const float cdfn = exact ? __fdiv_rn(cdf, total) : __fmul_rn(cdf, rcp);
-                pred = ((double)cdfn <= pos) && (j != K - 1);
-            }
-            const int ntrue = __syncthreads_count(pred);
-            const int nl = min(lo + ntrue * chunk, hi);
-            if (nl >= hi) lo = hi;
-            else { hi = min(nl + chunk, hi) - 1; lo = nl; }
-        }
-        enter = min(lo, K - 1);
-    }
-    // 16 consecutive positions per thread: running max of the marks, then across threads
-    const int kb = k0 + kPer * tid;
-    int m[kPer];
+    // ancestor of the position just before the tile: the particle whose run [c_{j-1}, c_j) covers it
+    const int enter = k0 ? p.tenter[(size_t)row * p.ntiles + tile] : 0;
     const bool vec = (K & 3) == 0;
+    int4 *s_tile4 = reinterpret_cast<int4 *>(s_tile);
     if (vec) {
 #pragma unroll
         for (int i = 0; i < kPer / 4; ++i) {
-            const int4 v = (kb + 4 * i < K) ? __ldg(reinterpret_cast<const int4 *>(p.marks + off + kb) + i) : make_int4(0, 0, 0, 0);
-            m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
+            const int c = tid + kTileThreads * i;
+            s_tile4[pad_chunk(c)] = (4 * c < n) ? reinterpret_cast<const int4 *>(p.marks + off + k0)[c] : make_int4(0, 0, 0, 0);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) m[i] = (kb + i < K) ? p.marks[off + kb + i] : 0;
+        for (int i = 0; i < kPer; ++i) {
+            const int k = tid + kTileThreads * i;
+            s_tile[pad_elem(k)] = (k < n) ? p.marks[off + k0 + k] : 0;
+        }
+    }
+    __syncthreads();
+    int m[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer / 4; ++i) {
+        const int4 v = s_tile4[pad_chunk(4 * tid + i)];
+        m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
     }
 #pragma unroll
     for (int i = 1; i < kPer; ++i) m[i] = max(m[i], m[i - 1]);
@@ -561,36 +648,37 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
     pre = max(pre, enter);
     for (int v = 0; v < warp; ++v) pre = max(pre, s_w[v]);
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) m[i] = max(m[i], pre);
+    for (int i = 0; i < kPer / 4; ++i)
+        s_tile4[pad_chunk(4 * tid + i)] = make_int4(max(m[4 * i], pre), max(m[4 * i + 1], pre), max(m[4 * i + 2], pre), max(m[4 * i + 3], pre));
+    __syncthreads();
     if (vec) {
-#pragma unroll
-        for (int i = 0; i < kPer / 4; ++i)
-            if (kb + 4 * i < K)
-                reinterpret_cast<int4 *>(p.idx + off + kb)[i] = make_int4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < kPer; ++i)
-            if (kb + i < K) p.idx[off + kb + i] = m[i];
-    }
-    if (!p.x_in) return;
-    if (p.D == 1 && vec) {
+        const bool gather1 = p.x_in && p.D == 1;
         const float *xin = p.x_in + off;
 #pragma unroll
-        for (int i = 0; i < kPer / 4; ++i)
-            if (kb + 4 * i < K)
-                reinterpret_cast<float4 *>(p.x_out + off + kb)[i] =
-                    make_float4(__ldg(xin + m[4 * i]), __ldg(xin + m[4 * i + 1]), __ldg(xin + m[4 * i + 2]), __ldg(xin + m[4 * i + 3]));
-        return;
-    }
+        for (int i = 0; i < kPer / 4; ++i) {
+            const int c = tid + kTileThreads * i;
+            if (4 * c < n) {
+                const int4 v = s_tile4[pad_chunk(c)];
+                reinterpret_cast<int4 *>(p.idx + off + k0)[c] = v;
+                if (gather1)
+                    reinterpret_cast<float4 *>(p.x_out + off + k0)[c] = make_float4(__ldg(xin + v.x), __ldg(xin + v.y), __ldg(xin + v.z), __ldg(xin + v.w));
+            }
+        }
+        if (!p.x_in || gather1) return;
+    } else {
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) s_tile[kPer * tid + i] = m[i];
-    __syncthreads();
+        for (int i = 0; i < kPer; ++i) {
+            const int k = tid + kTileThreads * i;
+            if (k < n) p.idx[off + k0 + k] = s_tile[pad_elem(k)];
+        }
+        if (!p.x_in) return;
+    }
     const int D = p.D;
     const float *xin = p.x_in + off * D;
     float *xout = p.x_out + (off + k0) * D;
     for (int e = tid; e < n * D; e += kTileThreads) {
         const int k = e / D;
-        xout[e] = __ldg(xin + (size_t)s_tile[k] * D + (e - k * D));
+        xout[e] = __ldg(xin + (size_t)s_tile[pad_elem(k)] * D + (e - k * D));
     }
 }
 
@@ -611,8 +699,9 @@ int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K)
 {
     const int64_t nt = (K + kTile - 1) / kTile;
     size_t bytes = 0;
-    bytes += align_up((size_t)B * K * 4) * 2;      // W, marks
-    bytes += align_up((size_t)B * nt * 4) * 2;     // tmax, tsum
+    bytes += align_up((size_t)B * K * 4);          // W
+    bytes += align_up((size_t)B * nt * 4) * 3;     // tmax, tsum, tenter
+    bytes += align_up((size_t)B * (nt + 1) * 8) * 2; // tbefore, tscale
     bytes += align_up((size_t)B * 4) * 4;          // rowmax, rowtotal, rowlse, rowbad
     const size_t nspans = (size_t)((K + 8191) / 8192); // room for the smallest span size
     bytes += align_up((size_t)B * ((size_t)2 << pairwise_depth((int)K)) * 4); // heap of node values
@@ -637,9 +726,13 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     p.W = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * K * 4);
-    p.marks = reinterpret_cast<int *>(ws); ws += align_up((size_t)B * K * 4);
+    p.marks = idx; // the run marks live in the idx output until the expansion rewrites each tile in place
     p.tmax = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
     p.tsum = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
+    p.tenter = reinterpret_cast<int *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
+    p.tbefore = reinterpret_cast<double *>(ws); ws += align_up((size_t)B * (p.ntiles + 1) * 8);
+    p.tscale = reinterpret_cast<double *>(ws); ws += align_up((size_t)B * (p.ntiles + 1) * 8);
+    p.tiled = exact ? 0 : 1;
     p.rowmax = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowtotal = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
     p.rowlse = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * 4);
@@ -661,7 +754,8 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     if (e == cudaSuccess && idx) e = cudaMemsetAsync(p.marks, 0, (size_t)B * K * 4, stream);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     const dim3 grid((unsigned)p.ntiles, (unsigned)B);
-    large_prep_kernel<<<grid, kTileThreads, 0, stream>>>(p);
+    if (exact) large_prep_kernel<false><<<grid, kTileThreads, 0, stream>>>(p);
+    else large_prep_kernel<true><<<grid, kTileThreads, 0, stream>>>(p);
     count_launch();
     if (exact) {
         const int nprobes = (int)((K + 63) / 64);
@@ -686,15 +780,14 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
             count_launch();
         }
     } else {
-        large_expsum_kernel<<<grid, kTileThreads, 0, stream>>>(p);
-        count_launch();
-        large_scan_kernel<<<grid, kTileThreads, 0, stream>>>(p);
+        large_rows_fast_kernel<<<(unsigned)B, 256, 0, stream>>>(p);
         count_launch();
     }
     if (idx) {
-        large_search_kernel<<<grid, kTileThreads, 0, stream>>>(p, exact ? 1 : 0);
+        if (exact) large_search_kernel<true, false><<<grid, kTileThreads, 0, stream>>>(p);
+        else large_search_kernel<false, true><<<grid, kTileThreads, 0, stream>>>(p);
         count_launch();
-        large_expand_kernel<<<grid, kTileThreads, 0, stream>>>(p, exact ? 1 : 0);
+        large_expand_kernel<<<grid, kTileThreads, 0, stream>>>(p);
         count_launch();
     }
     if (exact && idx && getenv("AESMC_DEBUG_STATS")) { // debugging aid: synchronises
