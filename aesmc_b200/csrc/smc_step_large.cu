@@ -67,6 +67,7 @@ struct LargeParams {
     float *vals;     // [B, heap_size] node values of numpy's pairwise tree, heap-indexed
     int *rowcnt;     // [B] number of particles equal to the row maximum
     unsigned long long *slots; // [B, nspans] (ready << 32 | carry bits) of each span of the chained scan
+    unsigned long long *lsums; // [B, nspans] (ready << 32 | bits of the span's own sum of weights)
     int *ticket;     // [0] span tickets, [1] padding; then rowcnt
     int *stats;      // [4] redo after a missed estimate / after a failed replay check / sequential spans
     int nspans, heap_depth, heap_size; // heap_depth: depth of the deepest leaf; heap_size = 2 << heap_depth
@@ -386,21 +387,6 @@ __global__ void __launch_bounds__(1024) large_fold_kernel(const LargeParams p)
 // chains overlap and 512-thread spans (two CTAs per SM, one hiding the other's barriers) have the better
 // throughput.  Measured on B200, K = 1e6: B = 8: 71 vs 106 us; B = 64: 331 vs 256 us.
 
-// (a) per-tile sums of the (approximate) normalised weights: the estimate of each span's entry value
-__global__ void __launch_bounds__(kTileThreads) large_wsum_kernel(const LargeParams p)
-{
-    __shared__ float s_f[32];
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    if (p.rowbad[row]) return;
-    const size_t off = (size_t)row * p.K;
-    const int k0 = tile * kTile, k1 = min(k0 + kTile, p.K);
-    const float shift = p.rowlse[row] * 1.4426950408889634f;
-    float part = 0.f;
-    for (int k = k0 + tid; k < k1; k += kTileThreads) part += exp2f(fmaf(p.log_w[off + k], 1.4426950408889634f, -shift));
-    part = block_allreduce(part, 0.f, OpSumF(), s_f);
-    if (tid == 0) p.tsum[(size_t)row * p.ntiles + tile] = part;
-}
-
 struct ChainedCarry {
     static constexpr bool kChained = true;
     float est, tol;
@@ -436,6 +422,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
     float *bufW = reinterpret_cast<float *>(bufW4);
     __shared__ ExactScanShared s_scan;
     __shared__ double s_d[32];
+    __shared__ float s_f[32];
     __shared__ float s_carry;
     __shared__ int s_ticket;
     // span-major tickets: whoever holds ticket t waits only for ticket t - B, which is already running
@@ -447,19 +434,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
     const float lse = p.rowlse[row];
     const int base = span * kSpan;
 
-    // estimate of the chain at the span start and its tolerance: the chain drifts from the real sum by
-    // ~sqrt(k) half-ulps on generic data (the bound k * 2^-24 is not used: a miss is detected and costs
-    // one redo of this span with the exact carry, never a wrong result)
-    double part = 0.0;
-    const int tiles_before = min(span * (kSpan / kTile), p.ntiles);
-    for (int t = tid; t < tiles_before; t += NT) part += (double)p.tsum[(size_t)row * p.ntiles + t];
-    part = block_allreduce(part, 0.0, OpSumD(), s_d);
-    ChainedCarry cc;
-    cc.est = (float)part;
-    cc.tol = cc.est * 5.9604644775390625e-08f * (8.0f * sqrtf((float)base) + 64.0f);
     unsigned long long *slots = p.slots + (size_t)row * p.nspans;
-    cc.prev = span ? slots + span - 1 : nullptr;
-    cc.mine = slots + span;
+    unsigned long long *lsums = p.lsums + (size_t)row * p.nspans;
+    float mysum = 0.f;
 
     // normalised weights of this span into the padded buffer (striped, coalesced), zeros past K
     if ((p.K & 3) == 0) {
@@ -477,14 +454,40 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
             np_expf_nonpos_pair(__fsub_rn(v[i].z, lse), __fsub_rn(v[i].w, lse), r.z, r.w);
             if (base + 4 * (tid + NT * i) >= p.K) r = make_float4(0.f, 0.f, 0.f, 0.f);
             bufW4[pad_chunk(tid + NT * i)] = r;
+            mysum += (r.x + r.y) + (r.z + r.w);
         }
     } else {
         for (int e = tid; e < kSpan; e += NT) {
             const int k = base + e;
-            bufW[pad_elem(e)] = (k < p.K) ? np_expf_nonpos(__fsub_rn(p.log_w[off + k], lse)) : 0.0f;
+            const float r = (k < p.K) ? np_expf_nonpos(__fsub_rn(p.log_w[off + k], lse)) : 0.0f;
+            bufW[pad_elem(e)] = r;
+            mysum += r;
         }
     }
-    __syncthreads();
+    // Estimate of the chain at the span start: every span publishes the plain sum of its weights as soon
+    // as it has them (no dependency), and sums those of its predecessors (all started earlier: tickets).
+    // The chain drifts from the real sum by ~sqrt(k) half-ulps on generic data; the tolerance is a
+    // multiple of that, not the bound k * 2^-24: a miss is detected by the walker and costs one redo of
+    // this span with the exact carry, never a wrong result.
+    mysum = block_allreduce(mysum, 0.f, OpSumF(), s_f); // also orders the buffer writes before the reads below
+    if (tid == 0) {
+        const unsigned long long v = (1ull << 32) | (unsigned long long)(unsigned)__float_as_int(mysum);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(lsums + span), "l"(v) : "memory");
+    }
+    double part = 0.0;
+    for (int t = tid; t < span; t += NT) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(lsums + t) : "memory");
+        } while ((v >> 32) == 0ull);
+        part += (double)__int_as_float((int)(unsigned)v);
+    }
+    part = block_allreduce(part, 0.0, OpSumD(), s_d);
+    ChainedCarry cc;
+    cc.est = (float)part;
+    cc.tol = cc.est * 5.9604644775390625e-08f * (8.0f * sqrtf((float)base) + 64.0f);
+    cc.prev = span ? slots + span - 1 : nullptr;
+    cc.mine = slots + span;
     float w[kScanItems];
     auto load_block = [&]() {
 #pragma unroll
@@ -705,7 +708,7 @@ int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K)
     bytes += align_up((size_t)B * 4) * 4;          // rowmax, rowtotal, rowlse, rowbad
     const size_t nspans = (size_t)((K + 8191) / 8192); // room for the smallest span size
     bytes += align_up((size_t)B * ((size_t)2 << pairwise_depth((int)K)) * 4); // heap of node values
-    bytes += align_up((size_t)B * 4 + (size_t)B * nspans * 8 + 8 + 16); // rowcnt, ticket, carry slots, stats (one memset)
+    bytes += align_up((size_t)B * 4 + (size_t)B * nspans * 16 + 8 + 16); // rowcnt, ticket, carry and sum slots, stats (one memset)
     return (int64_t)bytes;
 }
 
@@ -744,9 +747,10 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.heap_depth = pairwise_depth((int)K);
     p.heap_size = 2 << p.heap_depth;
     p.vals = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.heap_size * 4);
-    const size_t zero_bytes = (size_t)B * 4 + (size_t)B * p.nspans * 8 + 8 + 16;
+    const size_t zero_bytes = (size_t)B * 4 + (size_t)B * p.nspans * 16 + 8 + 16;
     p.slots = reinterpret_cast<unsigned long long *>(ws);
-    p.ticket = reinterpret_cast<int *>(ws + (size_t)B * p.nspans * 8);
+    p.lsums = p.slots + (size_t)B * p.nspans;
+    p.ticket = reinterpret_cast<int *>(ws + (size_t)B * p.nspans * 16);
     p.stats = p.ticket + 2;
     p.rowcnt = p.stats + 4;
     cudaError_t e = cudaMemsetAsync(p.rowbad, 0, (size_t)B * 4, stream);
@@ -765,8 +769,6 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
         large_fold_kernel<<<(unsigned)B, 1024, 0, stream>>>(p);
         count_launch();
         if (idx) {
-            large_wsum_kernel<<<grid, kTileThreads, 0, stream>>>(p);
-            count_launch();
             const size_t row_chunks = (size_t)span_threads * 4 + ((size_t)span_threads * 4 >> 3);
             const size_t smem_scan = row_chunks * 16 + (size_t)(8 * span_threads + 8) * 4;
             auto launch = [&](auto kernel) {
