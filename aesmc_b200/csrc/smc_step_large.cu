@@ -38,6 +38,7 @@ namespace aesmc {
 
 constexpr int kTile = 4096;
 constexpr int kTileThreads = 256;
+static_assert(kTile == 4096 && kTileThreads == 256, "tile-entry bookkeeping (c >> 12) and the 16-per-thread layouts assume 4096 / 256");
 
 struct LargeParams {
     const float *a, *b, *c;
