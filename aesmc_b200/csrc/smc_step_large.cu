@@ -28,6 +28,7 @@
 // one 8-byte carry slot per span.
 #include "common.cuh"
 #include "pairwise.cuh"
+#include "row_gather.cuh"
 #include "scan.cuh"
 #include "exact_scan.cuh"
 #include <algorithm>
@@ -49,6 +50,7 @@ struct LargeParams {
     const float *x_in;
     float *x_out;
     int D;
+    RowGather gather;
     int32_t *flags;
     float *W;        // [B, K]
     int *marks;      // [B, K]: the idx output doubles as the table of run marks
@@ -677,13 +679,7 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
         }
         if (!p.x_in) return;
     }
-    const int D = p.D;
-    const float *xin = p.x_in + off * D;
-    float *xout = p.x_out + (off + k0) * D;
-    for (int e = tid; e < n * D; e += kTileThreads) {
-        const int k = e / D;
-        xout[e] = __ldg(xin + (size_t)s_tile[pad_elem(k)] * D + (e - k * D));
-    }
+    gather_rows(p.x_in + off * p.D, p.x_out + (off + k0) * p.D, s_tile, n, p.gather);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -727,6 +723,7 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     LargeParams p;
     p.a = a; p.b = b; p.c = c; p.u = u; p.B = (int)B; p.K = (int)K; p.ntiles = (int)((K + kTile - 1) / kTile);
     p.log_w = log_w; p.lse = lse; p.idx = idx; p.x_in = x_in; p.x_out = x_out; p.D = (int)D; p.flags = flags;
+    p.gather = rows_gather_params(K, D);
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     p.W = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * K * 4);
