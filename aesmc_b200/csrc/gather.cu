@@ -16,42 +16,109 @@ __device__ __forceinline__ int load_index(const IdxT *idx_row, int k, int K, int
     return (int)id;
 }
 
-// dst[b,k,q] = src[b, idx[b,k], q] for q in [0, upr) units of type V per particle.
-template <typename V, typename IdxT>
-__global__ void gather_kernel(const V *__restrict__ src, const IdxT *__restrict__ idx, int B, int K, int upr,
-                              V *__restrict__ dst, int32_t *flags)
+// k = e / d by multiply-high with ceil(2^32 / d): exact for e < 2^32 / d; mul == ~0u: plain division
+struct FlatDiv {
+    unsigned d, mul;
+};
+static FlatDiv flat_div(int64_t n_rows, int64_t d)
 {
+    FlatDiv f;
+    f.d = (unsigned)d;
+    f.mul = d > 1 ? (unsigned)(((1ull << 32) + (unsigned long long)d - 1) / (unsigned long long)d) : 0u;
+    if ((unsigned long long)n_rows * (unsigned long long)d * (unsigned long long)d >= (1ull << 32)) f.mul = 0xffffffffu;
+    return f;
+}
+__device__ __forceinline__ int flat_row(int e, const FlatDiv f)
+{
+    return f.d == 1 ? e : (f.mul == 0xffffffffu ? (int)((unsigned)e / f.d) : (int)__umulhi((unsigned)e, f.mul));
+}
+
+// dst[b,k,q] = src[b, idx[b,k], q] for q in [0, upr) units of type V per particle: the (k, q) plane is swept
+// flat, so stores are fully coalesced; U loads in flight per thread.
+template <typename V, typename IdxT>
+__global__ void __launch_bounds__(256) gather_kernel(const V *__restrict__ src, const IdxT *__restrict__ idx, int B, int K,
+                                                     const FlatDiv upr, V *__restrict__ dst, int32_t *flags)
+{
+    constexpr int U = sizeof(V) >= 16 ? 2 : 4;
+    const int step = gridDim.x * blockDim.x, n = K * (int)upr.d;
     for (int row = blockIdx.y; row < B; row += gridDim.y) {
         const size_t roff = (size_t)row * K;
         const IdxT *irow = idx + roff;
-        const V *srow = src + roff * upr;
-        V *drow = dst + roff * upr;
-        const int n = K * upr;
-        if (upr == 1) {
-            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-                drow[k] = __ldg(srow + load_index(irow, k, K, flags));
-        } else {
-            for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-                const int k = e / upr, q = e - k * upr;
-                drow[e] = __ldg(srow + (size_t)load_index(irow, k, K, flags) * upr + q);
+        const V *srow = src + roff * upr.d;
+        V *drow = dst + roff * upr.d;
+        for (int e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += U * step) {
+            V v[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int e = e0 + q * step;
+                if (e < n) {
+                    const int k = flat_row(e, upr);
+                    v[q] = __ldg(srow + (size_t)load_index(irow, k, K, flags) * upr.d + (e - k * (int)upr.d));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int e = e0 + q * step;
+                if (e < n) drow[e] = v[q];
             }
         }
     }
+}
+
+// 4-byte particles (scalar float latents, the common case), K % 4 == 0, 16-byte aligned rows: four
+// outputs per thread, indices and results move as 16-byte vectors
+template <typename IdxT>
+__global__ void __launch_bounds__(256) gather4_kernel(const uint32_t *__restrict__ src, const IdxT *__restrict__ idx, int B,
+                                                      int K, uint32_t *__restrict__ dst, int32_t *flags)
+{
+    const int step = gridDim.x * blockDim.x, n4 = K >> 2;
+    for (int row = blockIdx.y; row < B; row += gridDim.y) {
+        const size_t roff = (size_t)row * K;
+        const IdxT *irow = idx + roff;
+        const uint32_t *srow = src + roff;
+        uint4 *drow = reinterpret_cast<uint4 *>(dst + roff);
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n4; c += step) {
+            long long i0, i1, i2, i3;
+            if (sizeof(IdxT) == 4) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(irow) + c);
+                i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+            } else {
+                const longlong2 v0 = __ldg(reinterpret_cast<const longlong2 *>(irow) + 2 * c);
+                const longlong2 v1 = __ldg(reinterpret_cast<const longlong2 *>(irow) + 2 * c + 1);
+                i0 = v0.x; i1 = v0.y; i2 = v1.x; i3 = v1.y;
+            }
+            if ((i0 | i1 | i2 | i3) < 0 || i0 >= K || i1 >= K || i2 >= K || i3 >= K) {
+                if (flags) atomicOr(flags, AESMC_FLAG_INDEX_RANGE);
+                i0 = i0 < 0 ? 0 : (i0 >= K ? K - 1 : i0); i1 = i1 < 0 ? 0 : (i1 >= K ? K - 1 : i1);
+                i2 = i2 < 0 ? 0 : (i2 >= K ? K - 1 : i2); i3 = i3 < 0 ? 0 : (i3 >= K ? K - 1 : i3);
+            }
+            drow[c] = make_uint4(__ldg(srow + i0), __ldg(srow + i1), __ldg(srow + i2), __ldg(srow + i3));
+        }
+    }
+}
+
+static unsigned gather_grid_x(int64_t n_per_row, int per_thread, int64_t B)
+{
+    // enough CTAs per row to cover it in one or two sweeps, fewer when there are plenty of rows
+    int64_t gx = (n_per_row + 256 * (int64_t)per_thread - 1) / (256 * (int64_t)per_thread);
+    const int64_t cap = B >= 1024 ? 4 : 64;
+    if (gx > cap) gx = cap;
+    return (unsigned)(gx < 1 ? 1 : gx);
 }
 
 template <typename V, typename IdxT>
 static void launch_gather_t(const void *src, const void *idx, int64_t B, int64_t K, int64_t upr, void *dst,
                             int32_t *flags, cudaStream_t st)
 {
-    const int threads = 256;
-    const int64_t n = K * upr;
-    unsigned gx = (unsigned)((n + threads - 1) / threads);
-    if (gx > 64) gx = 64;
-    if (gx < 1) gx = 1;
-    unsigned gy = (unsigned)(B < 65535 ? B : 65535);
-    dim3 grid(gx, gy);
-    gather_kernel<V, IdxT><<<grid, threads, 0, st>>>(static_cast<const V *>(src), static_cast<const IdxT *>(idx),
-                                                      (int)B, (int)K, (int)upr, static_cast<V *>(dst), flags);
+    const unsigned gy = (unsigned)(B < 65535 ? B : 65535);
+    const bool idx_aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    if (sizeof(V) == 4 && upr == 1 && (K & 3) == 0 && idx_aligned && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        gather4_kernel<IdxT><<<dim3(gather_grid_x(K / 4, 1, B), gy), 256, 0, st>>>(
+            static_cast<const uint32_t *>(src), static_cast<const IdxT *>(idx), (int)B, (int)K, static_cast<uint32_t *>(dst), flags);
+        return;
+    }
+    gather_kernel<V, IdxT><<<dim3(gather_grid_x(K * upr, 4, B), gy), 256, 0, st>>>(
+        static_cast<const V *>(src), static_cast<const IdxT *>(idx), (int)B, (int)K, flat_div(K, upr), static_cast<V *>(dst), flags);
 }
 
 int launch_gather_bytes(const void *src, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t row_bytes,
@@ -73,30 +140,94 @@ int launch_gather_bytes(const void *src, const void *idx, int idx_is_i64, int64_
     return check_launch("gather_kernel");
 }
 
-// Backward for non-decreasing indices (what the step kernel emits): the children of parent j form
-// one contiguous run of k.  The thread that sees a run start walks the run and sums it in k order --
-// the same order as the reference's CPU scatter_add -- so the result is deterministic and needs no
-// atomics.  gsrc must be zero-initialised (parents without children).
-template <typename T, typename IdxT>
-__global__ void gather_bwd_sorted_kernel(const T *__restrict__ g, const IdxT *__restrict__ idx, int B, int K, int D,
-                                         T *__restrict__ gsrc)
+// Backward for non-decreasing indices (what the step kernel emits): the children of parent j form one
+// contiguous run of k.  The (k, component) plane is swept flat; the thread that sees a run start sums the
+// run in k order -- the same order as the reference's CPU scatter_add, so the result is deterministic and
+// needs no atomics -- and also zero-fills the childless parents between the previous run's parent and its
+// own (the thread of the last particle fills those after it): every entry of gsrc is written exactly once,
+// no memset.  VT: vector of VW components of T (the widest that divides D).
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using v2 = float2; using v4 = float4; };
+template <> struct VecOf<double> { using v2 = double2; using v4 = double4; };
+__device__ __forceinline__ void vacc(float &a, float b) { a += b; }
+__device__ __forceinline__ void vacc(double &a, double b) { a += b; }
+__device__ __forceinline__ void vacc(float2 &a, float2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vacc(double2 &a, double2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vacc(float4 &a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// A thread owns P consecutive particles (P = 4 when a particle is one vector, else 1) and walks their
+// components Q at a time, so P * Q independent loads are in flight and the indices are read once per particle.
+// A run that is still open at the end of the thread's particles is followed to its end by that thread; the
+// particles of a run that began before the thread's first one belong to the thread that saw its start.
+template <typename VT, typename IdxT, int P, int Q>
+__global__ void __launch_bounds__(256) gather_bwd_sorted_kernel(const VT *__restrict__ g, const IdxT *__restrict__ idx, int B,
+                                                                int K, int D, VT *__restrict__ gsrc)
 {
+    const int step = gridDim.x * blockDim.x * P;
+    VT zero;
+    memset(&zero, 0, sizeof(VT));
     for (int row = blockIdx.y; row < B; row += gridDim.y) {
         const size_t roff = (size_t)row * K;
         const IdxT *irow = idx + roff;
-        const T *grow = g + roff * D;
-        T *orow = gsrc + roff * D;
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-            const IdxT j = irow[k];
-            if (k > 0 && irow[k - 1] == j) continue; // not a run start
-            if (j < 0 || j >= K) continue;
-            int end = k + 1;
-            while (end < K && irow[end] == j) ++end;
-            for (int d = 0; d < D; ++d) {
-                T acc = grow[(size_t)k * D + d];
-                for (int i = k + 1; i < end; ++i) acc += grow[(size_t)i * D + d];
-                orow[(size_t)j * D + d] = acc;
+        const VT *grow = g + roff * D;
+        VT *orow = gsrc + roff * D;
+        for (int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * P; k0 < K; k0 += step) {
+            const int np = min(P, K - k0);
+            int id[P + 2]; // ancestors of k0 - 1, k0 .. k0 + P - 1, k0 + P (clamped: memory safety only; -1 / K: none)
+            id[0] = -1;
+            if (k0) { const long long v = (long long)irow[k0 - 1]; id[0] = (int)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
+#pragma unroll
+            for (int p = 0; p <= P; ++p) {
+                id[p + 1] = K;
+                if (k0 + p < K) { const long long v = (long long)irow[k0 + p]; id[p + 1] = (int)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
             }
+            for (int q0 = 0; q0 < D; q0 += Q) {
+                VT gv[P][Q];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (p < np && q0 + q < D) gv[p][q] = grow[(size_t)(k0 + p) * D + q0 + q];
+                VT cur[Q];
+                bool open = false;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    if (p < np) {
+                        if (id[p + 1] != id[p]) { // run start
+                            open = true;
+#pragma unroll
+                            for (int q = 0; q < Q; ++q) cur[q] = gv[p][q];
+                        } else if (open) {
+#pragma unroll
+                            for (int q = 0; q < Q; ++q) vacc(cur[q], gv[p][q]);
+                        }
+                        if (open && p + 1 < np && id[p + 2] != id[p + 1]) { // the run ends inside the thread's particles
+#pragma unroll
+                            for (int q = 0; q < Q; ++q)
+                                if (q0 + q < D) orow[(size_t)id[p + 1] * D + q0 + q] = cur[q];
+                            open = false;
+                        }
+                    }
+                }
+                if (open) { // follow the last run to its end
+                    const int j = id[np];
+                    for (int i = k0 + np; i < K && (long long)irow[i] == (long long)j; ++i)
+#pragma unroll
+                        for (int q = 0; q < Q; ++q)
+                            if (q0 + q < D) vacc(cur[q], grow[(size_t)i * D + q0 + q]);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (q0 + q < D) orow[(size_t)j * D + q0 + q] = cur[q];
+                }
+            }
+            // childless parents: between the previous particle's ancestor and each run start of this thread,
+            // and after the last particle of the row
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (p < np && id[p + 1] != id[p])
+                    for (int e = (id[p] + 1) * D; e < id[p + 1] * D; ++e) orow[e] = zero;
+            if (k0 + np == K)
+                for (int e = (id[np] + 1) * D; e < K * D; ++e) orow[e] = zero;
         }
     }
 }
@@ -125,17 +256,25 @@ template <typename T>
 static int launch_gather_bwd_t(const T *g, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t D, T *gsrc,
                                int sorted, cudaStream_t st, const char *name)
 {
-    cudaError_t e = cudaMemsetAsync(gsrc, 0, sizeof(T) * (size_t)(B * K * D), st);
-    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     const int threads = 256;
     unsigned gy = (unsigned)(B < 65535 ? B : 65535);
     if (sorted) {
-        unsigned gx = (unsigned)((K + threads - 1) / threads);
-        if (gx > 64) gx = 64;
-        dim3 grid(gx ? gx : 1, gy);
-        if (idx_is_i64) gather_bwd_sorted_kernel<T, int64_t><<<grid, threads, 0, st>>>(g, static_cast<const int64_t *>(idx), (int)B, (int)K, (int)D, gsrc);
-        else gather_bwd_sorted_kernel<T, int32_t><<<grid, threads, 0, st>>>(g, static_cast<const int32_t *>(idx), (int)B, (int)K, (int)D, gsrc);
+        const uintptr_t align = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gsrc);
+        const int vw = (D % 4 == 0 && sizeof(T) == 4 && (align & 15) == 0) ? 4 : ((D % 2 == 0 && (align & (2 * sizeof(T) - 1)) == 0) ? 2 : 1);
+        const int dv = (int)(D / vw);
+        const dim3 grid(gather_grid_x(K, dv == 1 ? 4 : 1, B), gy);
+#define AESMC_BWD(VT, IT)                                                                                        \
+        do {                                                                                                     \
+            if (dv == 1) gather_bwd_sorted_kernel<VT, IT, 4, 1><<<grid, threads, 0, st>>>(reinterpret_cast<const VT *>(g), static_cast<const IT *>(idx), (int)B, (int)K, dv, reinterpret_cast<VT *>(gsrc)); \
+            else gather_bwd_sorted_kernel<VT, IT, 1, 4><<<grid, threads, 0, st>>>(reinterpret_cast<const VT *>(g), static_cast<const IT *>(idx), (int)B, (int)K, dv, reinterpret_cast<VT *>(gsrc)); \
+        } while (0)
+        if (vw == 4) { if (idx_is_i64) AESMC_BWD(float4, int64_t); else AESMC_BWD(float4, int32_t); }
+        else if (vw == 2) { if (idx_is_i64) AESMC_BWD(typename VecOf<T>::v2, int64_t); else AESMC_BWD(typename VecOf<T>::v2, int32_t); }
+        else { if (idx_is_i64) AESMC_BWD(T, int64_t); else AESMC_BWD(T, int32_t); }
+#undef AESMC_BWD
     } else {
+        cudaError_t e = cudaMemsetAsync(gsrc, 0, sizeof(T) * (size_t)(B * K * D), st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
         unsigned gx = (unsigned)((K * D + threads - 1) / threads);
         if (gx > 64) gx = 64;
         dim3 grid(gx ? gx : 1, gy);

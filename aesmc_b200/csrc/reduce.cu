@@ -25,17 +25,31 @@ template <> struct Acc<double> {
     __device__ static double mx(double a, double b) { return fmax(a, b); }
 };
 
+// Row sweep: f(v) for every element, 16-byte loads when the row allows (float32, K % 4 == 0, aligned).
+template <typename T, typename F>
+__device__ __forceinline__ void for_each_in_row(const T *__restrict__ row, int K, F f)
+{
+    if (sizeof(T) == 4 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        for (int c = threadIdx.x; c < (K >> 2); c += blockDim.x) {
+            const float4 v = r4[c];
+            f((T)v.x); f((T)v.y); f((T)v.z); f((T)v.w);
+        }
+    } else {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) f(row[k]);
+    }
+}
+
 // Row max and NaN flag; every thread of the CTA gets the result.
 template <typename T>
 __device__ __forceinline__ T row_max(const T *__restrict__ row, int K, T *scratch, int *has_nan)
 {
     T m = Acc<T>::ninf();
     int bad = 0;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const T v = row[k];
+    for_each_in_row(row, K, [&](T v) {
         bad |= (v != v);
         m = Acc<T>::mx(m, v);
-    }
+    });
     m = block_allreduce(m, Acc<T>::ninf(), typename Acc<T>::OpMax(), scratch);
     *has_nan = __syncthreads_or(bad);
     return m;
@@ -57,7 +71,7 @@ __global__ void logsumexp_rows_kernel(const T *__restrict__ lw, int B, int K, T 
             out = m; // all -inf -> -inf ; +inf present -> +inf (torch.logsumexp convention)
         } else {
             T s = 0;
-            for (int k = threadIdx.x; k < K; k += blockDim.x) s += Acc<T>::ex(r[k] - m);
+            for_each_in_row(r, K, [&](T v) { s += Acc<T>::ex(v - m); });
             s = block_allreduce(s, (T)0, typename Acc<T>::OpSum(), scratch);
             out = m + Acc<T>::lg(s);
         }
@@ -79,13 +93,22 @@ __global__ void lognormexp_kernel(const float *__restrict__ lw, int B, int K, fl
         else if (!(fabsf(m) < INFINITY)) lse = m;
         else {
             float s = 0.f;
-            for (int k = threadIdx.x; k < K; k += blockDim.x) s += expf(r[k] - m);
+            for_each_in_row(r, K, [&](float v) { s += expf(v - m); });
             s = block_allreduce(s, 0.f, OpSumF(), scratch);
             lse = m + logf(s);
         }
-        for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            const float d = r[k] - lse;
-            o[k] = exponentiate ? expf(d) : d;
+        if ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+            for (int c = threadIdx.x; c < (K >> 2); c += blockDim.x) {
+                float4 v = reinterpret_cast<const float4 *>(r)[c];
+                v.x -= lse; v.y -= lse; v.z -= lse; v.w -= lse;
+                if (exponentiate) { v.x = expf(v.x); v.y = expf(v.y); v.z = expf(v.z); v.w = expf(v.w); }
+                reinterpret_cast<float4 *>(o)[c] = v;
+            }
+        } else {
+            for (int k = threadIdx.x; k < K; k += blockDim.x) {
+                const float d = r[k] - lse;
+                o[k] = exponentiate ? expf(d) : d;
+            }
         }
     }
 }
@@ -99,11 +122,11 @@ __global__ void log_ess_kernel(const T *__restrict__ lw, int B, int K, T *__rest
         int bad;
         const T m = row_max(r, K, scratch, &bad);
         T s1 = 0, s2 = 0;
-        for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            const T e = Acc<T>::ex(r[k] - m);
+        for_each_in_row(r, K, [&](T v) {
+            const T e = Acc<T>::ex(v - m);
             s1 += e;
             s2 += e * e;
-        }
+        });
         s1 = block_allreduce(s1, (T)0, typename Acc<T>::OpSum(), scratch);
         s2 = block_allreduce(s2, (T)0, typename Acc<T>::OpSum(), scratch);
         // 2*(m + log s1) - (2m + log s2)
@@ -173,9 +196,27 @@ __global__ void weighted_moments_kernel(const float *__restrict__ x, const float
         int bad;
         const float m = row_max(r, K, scratch, &bad);
         float s = 0.f;
-        for (int k = threadIdx.x; k < K; k += blockDim.x) s += expf(r[k] - m);
+        for_each_in_row(r, K, [&](float v) { s += expf(v - m); });
         s = block_allreduce(s, 0.f, OpSumF(), scratch);
         const float lse = bad ? NAN : m + logf(s);
+        if (D == 1 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0) {
+            float a1 = 0.f, a2 = 0.f; // scalar latents: both tables move as 16-byte vectors
+            for (int c = threadIdx.x; c < (K >> 2); c += blockDim.x) {
+                const float4 l = reinterpret_cast<const float4 *>(r)[c], v = reinterpret_cast<const float4 *>(xr)[c];
+                const float w0 = expf(l.x - lse), w1 = expf(l.y - lse), w2 = expf(l.z - lse), w3 = expf(l.w - lse);
+                a1 = fmaf(w0, v.x, a1); a2 = fmaf(w0 * v.x, v.x, a2);
+                a1 = fmaf(w1, v.y, a1); a2 = fmaf(w1 * v.y, v.y, a2);
+                a1 = fmaf(w2, v.z, a1); a2 = fmaf(w2 * v.z, v.z, a2);
+                a1 = fmaf(w3, v.w, a1); a2 = fmaf(w3 * v.w, v.w, a2);
+            }
+            a1 = block_allreduce(a1, 0.f, OpSumF(), scratch);
+            a2 = block_allreduce(a2, 0.f, OpSumF(), scratch);
+            if (threadIdx.x == 0) {
+                mean[row] = a1;
+                if (second) second[row] = a2;
+            }
+            continue;
+        }
         for (int d0 = 0; d0 < D; d0 += 8) {
             float a1[8], a2[8];
 #pragma unroll

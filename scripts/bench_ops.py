@@ -1,0 +1,83 @@
+"""Throughput of the secondary kernels of the path (gather and its backward, step backward, row reductions,
+Normal.log_prob) at the headline shape, as algorithmic GB/s against the measured HBM peak.  One JSON line
+per op:
+
+    python scripts/bench_ops.py > profiles/r1_ops.jsonl
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aesmc_b200 import _lib, _ops  # noqa: E402
+
+dev = torch.device("cuda", 0)
+peak = 6550.1
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+B = K = 4096
+gen = torch.Generator(device=dev).manual_seed(0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def report(name, us, nbytes, **kw):
+    gbs = nbytes / us / 1e3
+    print(json.dumps(dict(op=name, B=B, K=K, us=round(us, 1), algorithmic_MB=round(nbytes / 1e6, 1),
+                          algorithmic_GBps=round(gbs, 1), frac_of_measured_hbm=round(gbs / peak, 3), **kw)), flush=True)
+
+
+tiny = torch.empty(32, dtype=torch.int32, device=dev)
+report("(host overhead of one C call: iota on 32 elements)", timed(lambda: _ops.iota_index(1, 32, dev)), 128)
+lw = torch.randn(B, K, device=dev, generator=gen) - 1.4
+u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
+flags = _ops.new_flags(dev)
+_, lse, idx, _ = _ops.smc_step(lw, None, None, u, None, flags, "exact", True)
+idx64 = idx.long()
+n = B * K
+
+for D in (1, 4, 10):
+    x = torch.randn(B, K, D, device=dev, generator=gen) if D > 1 else torch.randn(B, K, device=dev, generator=gen)
+    g = torch.randn_like(x)
+    report("gather D=%d (int32 idx)" % D, timed(lambda: _ops.gather(x, idx, True)), n * (4 + 8 * D), D=D)
+    report("gather D=%d (int64 idx)" % D, timed(lambda: _ops.gather(x, idx64, True)), n * (8 + 8 * D), D=D)
+    gsrc = torch.empty_like(g)
+    report("gather backward D=%d (sorted runs, C call)" % D,
+           timed(lambda: _lib.call("aesmc_gather_bwd_f32", _lib.ptr(g), _lib.ptr(idx), 0, B, K, D, _lib.ptr(gsrc), 1)),
+           n * (4 + 8 * D), D=D)
+
+a = lw.clone().requires_grad_(True)
+b = torch.randn(B, K, device=dev, generator=gen).requires_grad_(True)
+c = torch.randn(B, K, device=dev, generator=gen).requires_grad_(True)
+lw_o, lse_o, _, _ = _ops.smc_step(a, b, c, u, None, flags, "exact", True)
+g_lw, g_lse = torch.randn_like(lw_o), torch.randn_like(lse_o)
+report("step backward (g_a, g_b, g_c from g_log_w, g_lse)",
+       timed(lambda: torch.autograd.grad([lw_o, lse_o], [a, b, c], [g_lw, g_lse], retain_graph=True)), n * (4 + 4 + 8))
+report("logsumexp rows", timed(lambda: _ops.logsumexp_rows(lw)), n * 4)
+report("lognormexp rows (exp)", timed(lambda: _ops.lognormexp_rows(lw, True)), n * 8)
+report("log ESS rows", timed(lambda: _ops.log_ess_rows(lw)), n * 4)
+xs = torch.randn(B, K, device=dev, generator=gen)
+report("weighted moments (x, x^2)", timed(lambda: _ops.weighted_moments(xs, lw)), n * 8)
+acc = torch.zeros(B, K, device=dev)
+report("IS accumulate", timed(lambda: _ops.is_accumulate(lw, lw, lw, acc, lw, False)), n * 20)
+dist = torch.distributions.Normal(torch.randn(B, K, device=dev, generator=gen), 0.7, validate_args=False)
+report("Normal.log_prob (one kernel)", timed(lambda: _ops.normal_log_prob(dist, xs)), n * 12)
+report("compose genealogy index", timed(lambda: _ops.compose_index(idx, idx)), n * 12)

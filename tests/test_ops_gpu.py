@@ -61,14 +61,17 @@ def test_genealogy_known_answer(cuda):
 
 
 @pytest.mark.parametrize("sorted_rows", [True, False])
-@pytest.mark.parametrize("D", [1, 3, 10])
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 8, 10])
 def test_gather_backward(cuda, sorted_rows, D):
     rng = np.random.default_rng(3)
-    B, K = 5, 700
+    B, K = 6, 701
     idx = rng.integers(0, K, (B, K))
     if sorted_rows:
         idx = np.sort(idx, axis=1)
         idx[0] = 17                               # one parent takes everything
+        idx[1] = np.arange(K)                     # every parent exactly one child
+        idx[2, : K // 2] = 0                      # long run at the start, childless parents after it
+        idx[3] = np.sort(rng.integers(K - 3, K, K))  # everything at the end of the row
     x = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda).requires_grad_()
     g = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda)
     out = _ops.gather(x, torch.from_numpy(idx).int().to(cuda), sorted_rows=sorted_rows)
@@ -78,6 +81,19 @@ def test_gather_backward(cuda, sorted_rows, D):
         assert np.array_equal(x.grad.cpu().numpy(), ref)
     else:
         np.testing.assert_allclose(x.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("D", [1, 2, 5])
+def test_gather_backward_long_rows(cuda, D):
+    """Sorted backward on long rows: runs that span many threads and CTAs, odd K (no vector alignment)."""
+    rng = np.random.default_rng(D)
+    B, K = 2, 30011
+    idx = np.sort(rng.integers(0, K, (B, K)), axis=1)
+    idx[1, 100:9000] = idx[1, 100]               # a run spanning many threads
+    g = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda)
+    x = torch.zeros(B, K, D, device=cuda, requires_grad=True)
+    _ops.gather(x, torch.from_numpy(idx).int().to(cuda), sorted_rows=True).backward(g)
+    assert np.array_equal(x.grad.cpu().numpy(), oracle.resample_bwd(g.cpu().numpy(), idx))
 
 
 def test_step_backward_matches_torch_autograd(cuda):
