@@ -296,18 +296,6 @@ int launch_gather_bwd_f64(const double *g, const void *idx, int idx_is_i64, int6
     return launch_gather_bwd_t<double>(g, idx, idx_is_i64, B, K, D, gsrc, sorted, st, "gather_bwd<double>");
 }
 
-__global__ void compose_index_kernel(const int32_t *__restrict__ prev, const int32_t *__restrict__ cur, int B, int K,
-                                     int32_t *__restrict__ out)
-{
-    for (int row = blockIdx.y; row < B; row += gridDim.y) {
-        const size_t roff = (size_t)row * K;
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-            int c = cur[roff + k];
-            c = c < 0 ? 0 : (c >= K ? K - 1 : c);
-            out[roff + k] = __ldg(prev + roff + c);
-        }
-    }
-}
 __global__ void iota_index_kernel(int64_t n, int K, int32_t *__restrict__ out)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -333,12 +321,10 @@ static unsigned flat_blocks(int64_t n)
 
 int launch_compose_index(const int32_t *prev, const int32_t *cur, int64_t B, int64_t K, int32_t *out, cudaStream_t st)
 {
-    unsigned gx = (unsigned)((K + 255) / 256);
-    if (gx > 64) gx = 64;
-    dim3 grid(gx ? gx : 1, (unsigned)(B < 65535 ? B : 65535));
-    compose_index_kernel<<<grid, 256, 0, st>>>(prev, cur, (int)B, (int)K, out);
+    // out[b,k] = prev[b, cur[b,k]]: a gather of 4-byte particles (out-of-range entries of cur are clamped)
+    launch_gather_t<uint32_t, int32_t>(prev, cur, B, K, 1, out, nullptr, st);
     count_launch();
-    return check_launch("compose_index_kernel");
+    return check_launch("compose_index");
 }
 int launch_iota_index(int64_t B, int64_t K, int32_t *out, cudaStream_t st)
 {

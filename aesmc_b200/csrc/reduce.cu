@@ -6,6 +6,7 @@
 //   weighted moments               statistics.py:7-76 with f = x, x^2
 //   importance-sampling accumulate inference.py:156-157
 #include "common.cuh"
+#include <initializer_list>
 
 namespace aesmc {
 
@@ -258,50 +259,108 @@ struct NormalArgs {
     int scale_on_host, loc_on_host;
 };
 
-__device__ __forceinline__ float normal_operand(const float *p, int kind, int64_t i, int64_t row)
+// One row per blockIdx.y sweep (no division per element); VEC: K % 4 == 0 and 16-byte aligned tables, four
+// particles per thread.  Per-row and scalar operands are fetched once per row.
+struct NormalRow {
+    float v_row, mu_row;
+    bool v_table, mu_table;
+};
+__device__ __forceinline__ NormalRow normal_row(const NormalArgs &a, int row)
 {
-    return kind == 0 ? p[i] : (kind == 1 ? __ldg(p + row) : __ldg(p));
+    NormalRow r;
+    r.v_table = a.value_kind == 0;
+    r.v_row = r.v_table ? 0.f : __ldg(a.value + (a.value_kind == 1 ? row : 0));
+    r.mu_table = !a.loc_on_host && a.loc_kind == 0;
+    r.mu_row = a.loc_on_host ? a.loc_host : (r.mu_table ? 0.f : __ldg(a.loc + (a.loc_kind == 1 ? row : 0)));
+    return r;
 }
 
-__global__ void normal_log_prob_kernel(const NormalArgs a, int64_t n, int K, float *__restrict__ out)
+template <bool VEC>
+__global__ void __launch_bounds__(256) normal_log_prob_kernel(const NormalArgs a, int B, int K, float *__restrict__ out)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float two_var = 0.f, log_scale = a.log_scale_host;
     if (!a.scale_on_host) {
         const float sc = __ldg(a.scale_dev);
         two_var = __fmul_rn(2.0f, __fmul_rn(sc, sc));
         log_scale = logf(sc);
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t row = i / K;
-        const float v = normal_operand(a.value, a.value_kind, i, row);
-        const float mu = a.loc_on_host ? a.loc_host : normal_operand(a.loc, a.loc_kind, i, row);
+    auto lp = [&](float v, float mu) {
         const float d = __fsub_rn(v, mu);
         const float num = -__fmul_rn(d, d);
         const float q = a.scale_on_host ? __fmul_rn(num, a.inv_two_var_host) : __fdiv_rn(num, two_var);
-        out[i] = __fsub_rn(__fsub_rn(q, log_scale), a.half_log_2pi);
+        return __fsub_rn(__fsub_rn(q, log_scale), a.half_log_2pi);
+    };
+    const int step = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int row = blockIdx.y; row < B; row += gridDim.y) {
+        const NormalRow r = normal_row(a, row);
+        const size_t base = (size_t)row * K;
+        if (VEC) {
+            for (int c = first; c < (K >> 2); c += step) {
+                float4 v = make_float4(r.v_row, r.v_row, r.v_row, r.v_row), mu = make_float4(r.mu_row, r.mu_row, r.mu_row, r.mu_row);
+                if (r.v_table) v = reinterpret_cast<const float4 *>(a.value + base)[c];
+                if (r.mu_table) mu = reinterpret_cast<const float4 *>(a.loc + base)[c];
+                reinterpret_cast<float4 *>(out + base)[c] = make_float4(lp(v.x, mu.x), lp(v.y, mu.y), lp(v.z, mu.z), lp(v.w, mu.w));
+            }
+        } else {
+            for (int k = first; k < K; k += step)
+                out[base + k] = lp(r.v_table ? a.value[base + k] : r.v_row, r.mu_table ? a.loc[base + k] : r.mu_row);
+        }
     }
 }
 
 // backward: g_value = -g * d / var, and the per-particle terms of the loc / scale gradients
 //   g_loc_term = g * d / var          g_scale_term = g * (d^2 / scale^3 - 1 / scale)
-__global__ void normal_log_prob_bwd_kernel(const NormalArgs a, const float *__restrict__ g, float scale, int64_t n, int K,
-                                           float *__restrict__ g_value, float *__restrict__ g_loc,
-                                           float *__restrict__ g_scale)
+template <bool VEC>
+__global__ void __launch_bounds__(256) normal_log_prob_bwd_kernel(const NormalArgs a, const float *__restrict__ g, float scale,
+                                                                  int B, int K, float *__restrict__ g_value,
+                                                                  float *__restrict__ g_loc, float *__restrict__ g_scale)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float sc = a.scale_on_host ? scale : __ldg(a.scale_dev);
     const float inv_var = 1.0f / (sc * sc), inv_sc = 1.0f / sc;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t row = i / K;
-        const float v = normal_operand(a.value, a.value_kind, i, row);
-        const float mu = a.loc_on_host ? a.loc_host : normal_operand(a.loc, a.loc_kind, i, row);
-        const float d = v - mu, gi = g[i];
-        const float t = gi * d * inv_var;
-        if (g_value) g_value[i] = -t;
-        if (g_loc) g_loc[i] = t;
-        if (g_scale) g_scale[i] = gi * (d * d * inv_var * inv_sc - inv_sc);
+    const int step = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int row = blockIdx.y; row < B; row += gridDim.y) {
+        const NormalRow r = normal_row(a, row);
+        const size_t base = (size_t)row * K;
+        if (VEC) {
+            for (int c = first; c < (K >> 2); c += step) {
+                float4 v = make_float4(r.v_row, r.v_row, r.v_row, r.v_row), mu = make_float4(r.mu_row, r.mu_row, r.mu_row, r.mu_row);
+                if (r.v_table) v = reinterpret_cast<const float4 *>(a.value + base)[c];
+                if (r.mu_table) mu = reinterpret_cast<const float4 *>(a.loc + base)[c];
+                const float4 gi = reinterpret_cast<const float4 *>(g + base)[c];
+                const float d0 = v.x - mu.x, d1 = v.y - mu.y, d2 = v.z - mu.z, d3 = v.w - mu.w;
+                const float t0 = gi.x * d0 * inv_var, t1 = gi.y * d1 * inv_var, t2 = gi.z * d2 * inv_var, t3 = gi.w * d3 * inv_var;
+                if (g_value) reinterpret_cast<float4 *>(g_value + base)[c] = make_float4(-t0, -t1, -t2, -t3);
+                if (g_loc) reinterpret_cast<float4 *>(g_loc + base)[c] = make_float4(t0, t1, t2, t3);
+                if (g_scale)
+                    reinterpret_cast<float4 *>(g_scale + base)[c] =
+                        make_float4(gi.x * (d0 * d0 * inv_var * inv_sc - inv_sc), gi.y * (d1 * d1 * inv_var * inv_sc - inv_sc),
+                                    gi.z * (d2 * d2 * inv_var * inv_sc - inv_sc), gi.w * (d3 * d3 * inv_var * inv_sc - inv_sc));
+            }
+        } else {
+            for (int k = first; k < K; k += step) {
+                const size_t i = base + k;
+                const float d = (r.v_table ? a.value[i] : r.v_row) - (r.mu_table ? a.loc[i] : r.mu_row), gi = g[i];
+                const float t = gi * d * inv_var;
+                if (g_value) g_value[i] = -t;
+                if (g_loc) g_loc[i] = t;
+                if (g_scale) g_scale[i] = gi * (d * d * inv_var * inv_sc - inv_sc);
+            }
+        }
     }
+}
+
+static bool aligned16(std::initializer_list<const void *> ptrs)
+{
+    uintptr_t v = 0;
+    for (const void *p : ptrs) v |= reinterpret_cast<uintptr_t>(p);
+    return (v & 15) == 0;
+}
+static dim3 rows_grid2d(int64_t B, int64_t per_row_threads)
+{
+    int64_t gx = (per_row_threads + 255) / 256;
+    const int64_t cap = B >= 1024 ? 4 : 64;
+    if (gx > cap) gx = cap;
+    return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)(B < 65535 ? B : 65535));
 }
 
 // Exhaustive device-side check of np_expf_nonpos against np_expf over every float in [-104, -0] and
@@ -343,7 +402,9 @@ int normal_log_prob_f32(const float *value, int value_kind, const float *loc, in
     a.value = value; a.value_kind = value_kind; a.loc = loc; a.loc_kind = loc_kind; a.loc_host = loc_host;
     a.loc_on_host = (loc == nullptr); a.scale_dev = scale_dev; a.scale_on_host = (scale_dev == nullptr);
     a.inv_two_var_host = inv_two_var_host; a.log_scale_host = log_scale_host; a.half_log_2pi = half_log_2pi;
-    normal_log_prob_kernel<<<flat_grid(B * K, 256), 256, 0, st>>>(a, B * K, (int)K, out);
+    const bool vec = (K & 3) == 0 && aligned16({value_kind == 0 ? value : nullptr, (loc && loc_kind == 0) ? loc : nullptr, out});
+    if (vec) normal_log_prob_kernel<true><<<rows_grid2d(B, K / 4), 256, 0, st>>>(a, (int)B, (int)K, out);
+    else normal_log_prob_kernel<false><<<rows_grid2d(B, K), 256, 0, st>>>(a, (int)B, (int)K, out);
     count_launch();
     return check_launch("normal_log_prob_kernel");
 }
@@ -356,7 +417,9 @@ int normal_log_prob_bwd_f32(const float *value, int value_kind, const float *loc
     a.value = value; a.value_kind = value_kind; a.loc = loc; a.loc_kind = loc_kind; a.loc_host = loc_host;
     a.loc_on_host = (loc == nullptr); a.scale_dev = scale_dev; a.scale_on_host = (scale_dev == nullptr);
     a.inv_two_var_host = 0.f; a.log_scale_host = 0.f; a.half_log_2pi = 0.f;
-    normal_log_prob_bwd_kernel<<<flat_grid(B * K, 256), 256, 0, st>>>(a, g, scale_host, B * K, (int)K, g_value, g_loc, g_scale);
+    const bool vec = (K & 3) == 0 && aligned16({value_kind == 0 ? value : nullptr, (loc && loc_kind == 0) ? loc : nullptr, g, g_value, g_loc, g_scale});
+    if (vec) normal_log_prob_bwd_kernel<true><<<rows_grid2d(B, K / 4), 256, 0, st>>>(a, g, scale_host, (int)B, (int)K, g_value, g_loc, g_scale);
+    else normal_log_prob_bwd_kernel<false><<<rows_grid2d(B, K), 256, 0, st>>>(a, g, scale_host, (int)B, (int)K, g_value, g_loc, g_scale);
     count_launch();
     return check_launch("normal_log_prob_bwd_kernel");
 }
