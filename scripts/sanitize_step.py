@@ -1,5 +1,6 @@
 """Small driver for compute-sanitizer (memcheck / racecheck / synccheck) over every step-kernel variant:
-register-blocked (regular and irregular K, D = 1 and D > 1), generic, multi-CTA, fused, both modes."""
+register-blocked (regular and irregular K, D = 1 and D > 1), generic, multi-CTA (both span sizes of the chained
+exact scan, vector and scalar tails), fused, both modes; then the gather / backward / row-reduction kernels."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ from aesmc_b200 import _ops, fused  # noqa: E402
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(0)
 for mode in ("exact", "fast"):
-    for B, K, D in [(5, 4096, 1), (3, 1000, 1), (3, 2048, 3), (2, 1023, 1), (2, 30000, 1), (1, 70000, 2)]:
+    for B, K, D in [(5, 4096, 1), (3, 1000, 1), (3, 2048, 3), (2, 1023, 1), (2, 30000, 1), (1, 70000, 2), (25, 33000, 1), (2, 40003, 1)]:
         a, b, c = [torch.randn(B, K, device=dev, generator=gen) for _ in range(3)]
         x = torch.randn(B, K, D, device=dev, generator=gen) if D > 1 else torch.randn(B, K, device=dev, generator=gen)
         u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
@@ -27,4 +28,24 @@ for mode in ("exact", "fast"):
         r = fused.infer_fused(model, obs, 512, return_log_marginal_likelihood=True, resampling_mode=mode)
     torch.cuda.synchronize()
     assert torch.isfinite(r["log_marginal_likelihood"]).all()
+from aesmc_b200 import statistics  # noqa: E402
+for D in (1, 2, 4, 10):
+    B, K = 3, 1001 if D == 1 else 1000
+    x = (torch.randn(B, K, D, device=dev, generator=gen) if D > 1 else torch.randn(B, K, device=dev, generator=gen)).requires_grad_()
+    idx = torch.sort(torch.randint(0, K, (B, K), device=dev, generator=gen), dim=1).values
+    for ix, srt in ((idx.int(), True), (idx, True), (idx.flip(1).contiguous(), False)):
+        out = _ops.gather(x, ix, srt)
+        out.backward(torch.ones_like(out))
+lw = torch.randn(5, 4096, device=dev, generator=gen)
+_ops.logsumexp_rows(lw); _ops.lognormexp_rows(lw, True); _ops.log_ess_rows(lw)
+_ops.weighted_moments(torch.randn(5, 4096, device=dev, generator=gen), lw)
+_ops.weighted_moments(torch.randn(5, 4096, 3, device=dev, generator=gen), lw)
+_ops.logsumexp_rows(lw[:, :1001].contiguous()); _ops.log_ess_rows(lw[:, :1001].contiguous())
+for K in (4096, 1001):
+    v = torch.randn(5, K, device=dev, generator=gen).requires_grad_()
+    mu = torch.randn(5, K, device=dev, generator=gen).requires_grad_()
+    lp = _ops.normal_log_prob(torch.distributions.Normal(mu, 0.7, validate_args=False), v)
+    lp.sum().backward()
+_ops.compose_index(idx.int(), idx.int())
+torch.cuda.synchronize()
 print("sanitize driver ok")
