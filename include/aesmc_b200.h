@@ -72,9 +72,11 @@ int aesmc_smc_step_f32(const float *lp_a, const float *lp_b, const float *lp_c, 
                        void *stream);
 
 /*
- * Rows too large for one CTA (K > aesmc_max_particles_single_cta()) run a multi-CTA pipeline that needs
- * caller-allocated device scratch: aesmc_smc_step_workspace_bytes(B, K) bytes (0 when not needed), 256-byte
- * aligned, passed to aesmc_smc_step_ws_f32 (identical to aesmc_smc_step_f32 otherwise).
+ * Rows beyond the register-blocked single-CTA kernel (K > 16 384, or 8 192 < K with K % 4 != 0) run a
+ * multi-CTA pipeline that needs caller-allocated device scratch: aesmc_smc_step_workspace_bytes(B, K) bytes
+ * (0 when not needed), 256-byte aligned, passed to aesmc_smc_step_ws_f32 (identical to aesmc_smc_step_f32
+ * otherwise).  Without a workspace, rows up to aesmc_max_particles_single_cta() still run (a slower
+ * shared-memory kernel, 3-4x behind the multi-CTA path); longer rows return AESMC_ERR_BAD_ARG.
  */
 int64_t aesmc_smc_step_workspace_bytes(int64_t B, int64_t K);
 int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_c, const double *u,

@@ -254,7 +254,26 @@ def test_exact_parallel_cumsum_stress(cuda, K):
     assert bad.size == 0, "rows with index mismatches: %s" % bad[:10]
 
 
-@pytest.mark.parametrize("B,K,D", [(2, 27000, 1), (3, 40000, 3), (2, 65536, 1), (2, 100003, 1), (1, 262144, 2), (2, 1000000, 1)])
+def test_shared_memory_kernel_without_workspace(cuda):
+    """aesmc_smc_step_f32 (no workspace) on a row beyond the register-blocked kernel: the shared-memory
+    kernel still serves it, bit-equal to the oracle (with a workspace such rows take the multi-CTA path)."""
+    rng = np.random.default_rng(5)
+    B, K = 2, 20000
+    lw = (rng.standard_normal((B, K)) * 2).astype(np.float32)
+    u = rng.random(B)
+    d_lw, d_u = dev_f32(lw, cuda), dev_f64(u, cuda)
+    log_w, lse = torch.empty_like(d_lw), torch.empty(B, device=cuda)
+    idx = torch.empty(B, K, dtype=torch.int32, device=cuda)
+    flags = _ops.new_flags(cuda)
+    _lib.call("aesmc_smc_step_f32", d_lw.data_ptr(), None, None, d_u.data_ptr(), B, K, log_w.data_ptr(), lse.data_ptr(),
+              idx.data_ptr(), None, None, 1, flags.data_ptr(), _ops.mode_code("exact"))
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw, u, return_parts=True)
+    assert int(flags.item()) == 0 and st == 0
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+    assert np.array_equal(idx.cpu().numpy(), np.minimum(idx_ref, K - 1).astype(np.int32))
+
+
+@pytest.mark.parametrize("B,K,D", [(2, 9001, 2), (3, 20000, 1), (2, 27000, 1), (3, 40000, 3), (2, 65536, 1), (2, 100003, 1), (1, 262144, 2), (2, 1000000, 1)])
 def test_multi_cta_path_vs_oracle(cuda, B, K, D):
     """Rows too large for one CTA (BASELINE config 5, K up to 1e6): exact mode bit-equal to the oracle,
     fast mode within the documented flip rate; log-weights, lse and the gather checked as well."""
