@@ -155,31 +155,47 @@ __device__ __forceinline__ void vacc(float2 &a, float2 b) { a.x += b.x; a.y += b
 __device__ __forceinline__ void vacc(double2 &a, double2 b) { a.x += b.x; a.y += b.y; }
 __device__ __forceinline__ void vacc(float4 &a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+__device__ __forceinline__ float vshfl(float v, int m) { return __shfl_xor_sync(kFull, v, m); }
+__device__ __forceinline__ double vshfl(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+__device__ __forceinline__ float2 vshfl(float2 v, int m) { return make_float2(vshfl(v.x, m), vshfl(v.y, m)); }
+__device__ __forceinline__ double2 vshfl(double2 v, int m) { return make_double2(vshfl(v.x, m), vshfl(v.y, m)); }
+__device__ __forceinline__ float4 vshfl(float4 v, int m) { return make_float4(vshfl(v.x, m), vshfl(v.y, m), vshfl(v.z, m), vshfl(v.w, m)); }
+
 // A thread owns P consecutive particles (P = 4 when a particle is one vector, else 1) and walks their
 // components Q at a time, so P * Q independent loads are in flight and the indices are read once per particle.
-// A run that is still open at the end of the thread's particles is followed to its end by that thread; the
-// particles of a run that began before the thread's first one belong to the thread that saw its start.
+// A run that is still open at the end of the thread's particles is followed by that thread for up to kTail
+// more children (k order, the reference's scatter_add order); the particles of a run that began before the
+// thread's first one belong to the thread that saw its start.  Longer runs -- collapsed weights put thousands
+// of children under one parent, which a single thread would chase for hundreds of microseconds -- and long
+// stretches of childless parents are finished by the whole warp: coalesced 32-particle windows, per-lane
+// partial sums, one fixed shuffle tree (deterministic; the summation order of those runs is no longer k).
+constexpr int kTail = 16;
+
 template <typename VT, typename IdxT, int P, int Q>
-__global__ void __launch_bounds__(256) gather_bwd_sorted_kernel(const VT *__restrict__ g, const IdxT *__restrict__ idx, int B,
+__global__ void __launch_bounds__(256, sizeof(VT) * Q <= 8 ? 6 : 4) gather_bwd_sorted_kernel(const VT *__restrict__ g, const IdxT *__restrict__ idx, int B,
                                                                 int K, int D, VT *__restrict__ gsrc)
 {
-    const int step = gridDim.x * blockDim.x * P;
+    constexpr int kWin = Q == 1 ? 4 : 1; // windows in flight in the cooperative section (register budget)
+    const int step = gridDim.x * blockDim.x * P, lane = threadIdx.x & 31;
     VT zero;
     memset(&zero, 0, sizeof(VT));
+    auto clampi = [K](long long v) { return (int)(v < 0 ? 0 : (v >= K ? K - 1 : v)); };
     for (int row = blockIdx.y; row < B; row += gridDim.y) {
         const size_t roff = (size_t)row * K;
         const IdxT *irow = idx + roff;
         const VT *grow = g + roff * D;
         VT *orow = gsrc + roff * D;
-        for (int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * P; k0 < K; k0 += step) {
-            const int np = min(P, K - k0);
+        // warp-uniform trip count: the cooperative sections below need every lane
+        for (int kw = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * P; kw < K; kw += step) {
+            const int k0 = kw + lane * P;
+            const int np = max(0, min(P, K - k0));
             int id[P + 2]; // ancestors of k0 - 1, k0 .. k0 + P - 1, k0 + P (clamped: memory safety only; -1 / K: none)
             id[0] = -1;
-            if (k0) { const long long v = (long long)irow[k0 - 1]; id[0] = (int)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
+            if (k0 && np) id[0] = clampi((long long)irow[k0 - 1]);
 #pragma unroll
             for (int p = 0; p <= P; ++p) {
                 id[p + 1] = K;
-                if (k0 + p < K) { const long long v = (long long)irow[k0 + p]; id[p + 1] = (int)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
+                if (k0 + p < K) id[p + 1] = clampi((long long)irow[k0 + p]);
             }
             for (int q0 = 0; q0 < D; q0 += Q) {
                 VT gv[P][Q];
@@ -189,6 +205,8 @@ __global__ void __launch_bounds__(256) gather_bwd_sorted_kernel(const VT *__rest
                     for (int q = 0; q < Q; ++q)
                         if (p < np && q0 + q < D) gv[p][q] = grow[(size_t)(k0 + p) * D + q0 + q];
                 VT cur[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) cur[q] = zero;
                 bool open = false;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -209,25 +227,87 @@ __global__ void __launch_bounds__(256) gather_bwd_sorted_kernel(const VT *__rest
                         }
                     }
                 }
-                if (open) { // follow the last run to its end
-                    const int j = id[np];
-                    for (int i = k0 + np; i < K && (long long)irow[i] == (long long)j; ++i)
+                int j = 0; // ancestor of the thread's last particle (no dynamic indexing: id[] stays in registers)
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    if (p + 1 == np) j = id[p + 1];
+                int next = k0 + np; // first particle not yet accounted for
+                bool long_run = false;
+                if (open) { // follow the last run
+                    int cnt = 0;
+                    for (; next < K && cnt < kTail && (long long)irow[next] == (long long)j; ++next, ++cnt)
 #pragma unroll
                         for (int q = 0; q < Q; ++q)
-                            if (q0 + q < D) vacc(cur[q], grow[(size_t)i * D + q0 + q]);
+                            if (q0 + q < D) vacc(cur[q], grow[(size_t)next * D + q0 + q]);
+                    long_run = cnt == kTail && next < K && (long long)irow[next] == (long long)j;
+                    if (!long_run) {
 #pragma unroll
-                    for (int q = 0; q < Q; ++q)
-                        if (q0 + q < D) orow[(size_t)j * D + q0 + q] = cur[q];
+                        for (int q = 0; q < Q; ++q)
+                            if (q0 + q < D) orow[(size_t)j * D + q0 + q] = cur[q];
+                    }
+                }
+                for (unsigned pend = __ballot_sync(kFull, long_run); pend; pend &= pend - 1) {
+                    const int src = __ffs(pend) - 1;
+                    const int jj = __shfl_sync(kFull, j, src);
+                    int start = __shfl_sync(kFull, next, src);
+                    VT part[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) part[q] = zero;
+                    for (;;) { // idx is sorted: the lanes still inside the run form a prefix of each 32-particle window
+                        bool in[kWin];
+#pragma unroll
+                        for (int w = 0; w < kWin; ++w) { // kWin windows in flight: the exit test is a full round trip
+                            const int i = start + 32 * w + lane;
+                            in[w] = i < K && (long long)irow[i] == (long long)jj;
+                        }
+#pragma unroll
+                        for (int w = 0; w < kWin; ++w) {
+                            const int i = start + 32 * w + lane;
+                            if (in[w]) {
+#pragma unroll
+                                for (int q = 0; q < Q; ++q)
+                                    if (q0 + q < D) vacc(part[q], grow[(size_t)i * D + q0 + q]);
+                            }
+                        }
+                        if (__ballot_sync(kFull, in[kWin - 1]) != kFull) break;
+                        start += 32 * kWin;
+                    }
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                        for (int m = 16; m > 0; m >>= 1) vacc(part[q], vshfl(part[q], m));
+                        if (lane == src && q0 + q < D) {
+                            vacc(cur[q], part[q]);
+                            orow[(size_t)jj * D + q0 + q] = cur[q];
+                        }
+                    }
                 }
             }
-            // childless parents: between the previous particle's ancestor and each run start of this thread,
-            // and after the last particle of the row
+            // childless parents: between the previous particle's ancestor and each run start of this thread, and
+            // after the last particle of the row; long stretches are left to the whole warp
+            int gap_lo = 0, gap_hi = 0; // at most one deferred stretch per thread and pass is kept; others are filled here
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                if (p < np && id[p + 1] != id[p])
-                    for (int e = (id[p] + 1) * D; e < id[p + 1] * D; ++e) orow[e] = zero;
-            if (k0 + np == K)
-                for (int e = (id[np] + 1) * D; e < K * D; ++e) orow[e] = zero;
+            for (int p = 0; p < P; ++p) {
+                if (p < np && id[p + 1] != id[p]) {
+                    const int lo = (id[p] + 1) * D, hi = id[p + 1] * D;
+                    if (hi - lo > 64 && gap_hi == gap_lo) { gap_lo = lo; gap_hi = hi; }
+                    else for (int e = lo; e < hi; ++e) orow[e] = zero;
+                }
+            }
+            if (np && k0 + np == K) {
+                int jl = 0;
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    if (p + 1 == np) jl = id[p + 1];
+                const int lo = (jl + 1) * D, hi = K * D;
+                if (hi - lo > 64 && gap_hi == gap_lo) { gap_lo = lo; gap_hi = hi; }
+                else for (int e = lo; e < hi; ++e) orow[e] = zero;
+            }
+            for (unsigned pend = __ballot_sync(kFull, gap_hi > gap_lo); pend; pend &= pend - 1) {
+                const int src = __ffs(pend) - 1;
+                const int lo = __shfl_sync(kFull, gap_lo, src), hi = __shfl_sync(kFull, gap_hi, src);
+                for (int e = lo + lane; e < hi; e += 32) orow[e] = zero;
+            }
         }
     }
 }

@@ -64,6 +64,13 @@ for D in (1, 4, 10):
            timed(lambda: _lib.call("aesmc_gather_bwd_f32", _lib.ptr(g), _lib.ptr(idx), 0, B, K, D, _lib.ptr(gsrc), 1)),
            n * (4 + 8 * D), D=D)
 
+# collapsed weights (what training sees early on): a few parents own thousands of children each
+_, _, idx_c, _ = _ops.smc_step(lw * 8.0, None, None, u, None, flags, "exact", True)
+g1 = torch.randn(B, K, device=dev, generator=gen)
+gs1 = torch.empty_like(g1)
+report("gather backward D=1, collapsed weights (max run %d)" % int(torch.bincount(idx_c[0].long()).max()),
+       timed(lambda: _lib.call("aesmc_gather_bwd_f32", _lib.ptr(g1), _lib.ptr(idx_c), 0, B, K, 1, _lib.ptr(gs1), 1)), n * 12)
+
 a = lw.clone().requires_grad_(True)
 b = torch.randn(B, K, device=dev, generator=gen).requires_grad_(True)
 c = torch.randn(B, K, device=dev, generator=gen).requires_grad_(True)

@@ -77,10 +77,16 @@ def test_gather_backward(cuda, sorted_rows, D):
     out = _ops.gather(x, torch.from_numpy(idx).int().to(cuda), sorted_rows=sorted_rows)
     out.backward(g)
     ref = oracle.resample_bwd(g.cpu().numpy(), idx)
-    if sorted_rows:   # run-ordered summation == the reference's CPU scatter_add order
-        assert np.array_equal(x.grad.cpu().numpy(), ref)
+    got = x.grad.cpu().numpy()
+    if sorted_rows:
+        # runs of up to 16 children are summed in k order == the reference's CPU scatter_add order, bit for bit;
+        # longer runs (collapsed weights) are finished by a warp-wide fixed-shape reduction
+        short = np.array([np.bincount(idx[b], minlength=K).max() <= 16 for b in range(B)])
+        assert short.sum() >= 3 and (~short).sum() >= 3
+        assert np.array_equal(got[short], ref[short])
+        np.testing.assert_allclose(got[~short], ref[~short], rtol=1e-5, atol=2e-5)
     else:
-        np.testing.assert_allclose(x.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("D", [1, 2, 5])
@@ -93,7 +99,9 @@ def test_gather_backward_long_rows(cuda, D):
     g = torch.from_numpy(rng.standard_normal((B, K, D)).astype(np.float32)).to(cuda)
     x = torch.zeros(B, K, D, device=cuda, requires_grad=True)
     _ops.gather(x, torch.from_numpy(idx).int().to(cuda), sorted_rows=True).backward(g)
-    assert np.array_equal(x.grad.cpu().numpy(), oracle.resample_bwd(g.cpu().numpy(), idx))
+    ref = oracle.resample_bwd(g.cpu().numpy(), idx)
+    assert np.array_equal(x.grad.cpu().numpy()[0], ref[0])          # short runs: the reference's order, bit for bit
+    np.testing.assert_allclose(x.grad.cpu().numpy()[1], ref[1], rtol=1e-5, atol=1e-4)  # the 8 900-child run: warp reduction
 
 
 def test_step_backward_matches_torch_autograd(cuda):
