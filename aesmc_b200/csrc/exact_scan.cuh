@@ -108,9 +108,21 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         const int el = __float_as_int(lo) >> 23, eh = __float_as_int(hi) >> 23;
         if (el == eh) eb = el;
     }
-    // a block of zero weights (padding past K, -inf log-weights) is the identity map in every binade:
-    // eb = -1, so that the tail of a row, whose sum sits at the binade boundary 1.0, is not walked
-    if (ls == 0.f) eb = -1;
+    // A block whose weights are all absorbed -- each below half an ulp of the running sum, so that every
+    // RN(s + w) returns s -- is the identity map in every binade (eb = -1); zero weights (padding past K, -inf
+    // log-weights) are the trivial case.  This is what keeps the plateaus of a collapsed weight vector out of
+    // the walker: after the last heavy particle the sum sits within a few ulps of the binade boundary 1.0, and
+    // every block there would otherwise be "mixed".  ls < lo * 2^-26 bounds every weight of the block by
+    // 2^-25 of a lower bound of the entry value, i.e. strictly below half an ulp of anything the sum can be.
+    if (ls == 0.f || ls < __fmul_rd(lo, 1.4901161193847656e-08f)) eb = -1;
+    // ... and it joins the pure run it follows (within the warp) as a pure block of that binade -- its scaled
+    // chain below yields the map (0, 0) -- instead of cutting the run in two: a collapsed row alternates
+    // absorbed and live blocks and would otherwise hand the walker one segment per block
+    {
+        const unsigned live = __ballot_sync(kFull, eb != -1), below = live & ((1u << lane) - 1u);
+        const int e_prev = __shfl_sync(kFull, eb, below ? 31 - __clz(below) : 0);
+        if (eb == -1 && below && e_prev > 0) eb = e_prev;
+    }
 
     // ---- pure block -> (c0, c1): the scaled chain from an even and an odd start -------------------
     const float scale = __int_as_float((277 - (eb > 0 ? eb : 127)) << 23); // 2^(23 - e), exact multiplier

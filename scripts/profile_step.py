@@ -18,11 +18,12 @@ ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--particles", type=int, default=4096)
 ap.add_argument("--dim", type=int, default=1)
 ap.add_argument("--launches", type=int, default=6)
+ap.add_argument("--scale", type=float, default=1.0, help="spread of the synthetic log-weights (8: collapsed weights)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 B, K, D = args.batch, args.particles, args.dim
 gen = torch.Generator(device=dev).manual_seed(0)
-sets = [[torch.randn(B, K, device=dev, generator=gen) - 1.4 for _ in range(3)] for _ in range(2)]
+sets = [[args.scale * torch.randn(B, K, device=dev, generator=gen) - 1.4 for _ in range(3)] for _ in range(2)]
 x = [torch.randn(B, K, D, device=dev, generator=gen), torch.empty(B, K, D, device=dev)]
 u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
 log_w = torch.empty(B, K, device=dev)
