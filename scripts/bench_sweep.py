@@ -2,6 +2,11 @@
 batch (and the headline shape for comparison).  Prints one JSON line per (B, K, mode):
 
     python scripts/bench_sweep.py [--steps 20] > profiles/r1_sweep.jsonl
+
+Under torchrun (one rank per GPU) every rank runs its own B rows -- rows are independent, the path has no
+collective -- and rank 0 reports the whole job (N * B rows over the slowest rank's time):
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/bench_sweep.py
 """
 import argparse
 import json
@@ -21,7 +26,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)   # T
 ap.add_argument("--cpu", action="store_true", help="also time the C oracle (1 thread) on 2 rows")
 args = ap.parse_args()
-dev = torch.device("cuda", 0)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 peak = 6550.1
 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -52,19 +63,27 @@ for B, K in [(8, 1000), (64, 1000), (8, 10000), (64, 10000), (8, 100000), (64, 1
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         e0.record()
         for _ in range(reps):
             run()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (reps * T)
-        gbs = 28.0 * B * K / (ms * 1e-3) / 1e9
-        line = {"B": B, "K": K, "T": T, "mode": mode, "us_per_step": round(ms * 1e3, 2),
-                "particle_steps_per_s": B * K / (ms * 1e-3), "algorithmic_GBps": round(gbs, 1),
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gbs = 28.0 * B * K / (ms * 1e-3) / 1e9  # per GPU
+        line = {"n_gpus": world, "B": B * world, "B_per_gpu": B, "K": K, "T": T, "mode": mode, "us_per_step": round(ms * 1e3, 2),
+                "particle_steps_per_s": world * B * K / (ms * 1e-3), "algorithmic_GBps_per_gpu": round(gbs, 1),
                 "frac_of_measured_hbm": round(gbs / peak, 4), "path": "multi-CTA" if ws_bytes else "single-CTA",
                 "flags": int(flags.item())}
-        print(json.dumps(line), flush=True)
-    if args.cpu and K >= 1000 and B == 8:
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    if args.cpu and K >= 1000 and B == 8 and rank == 0:
         from oracle import core as oracle
         rng = np.random.default_rng(0)
         rows = 2
@@ -77,3 +96,5 @@ for B, K in [(8, 1000), (64, 1000), (8, 10000), (64, 10000), (8, 100000), (64, 1
         print(json.dumps({"K": K, "mode": "cpu oracle (C, 1 thread)", "particle_steps_per_s": rows * K * T / dt}), flush=True)
     del ring, arena, log_w, idx, ws
     torch.cuda.empty_cache()
+if world > 1:
+    dist.destroy_process_group()
