@@ -13,7 +13,6 @@ import json
 import math
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -24,7 +23,6 @@ from aesmc_b200 import _lib, _ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)   # T
-ap.add_argument("--cpu", action="store_true", help="also time the C oracle (1 thread) on 2 rows")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -83,17 +81,6 @@ for B, K in [(8, 1000), (64, 1000), (8, 10000), (64, 10000), (8, 100000), (64, 1
                 "flags": int(flags.item())}
         if rank == 0:
             print(json.dumps(line), flush=True)
-    if args.cpu and K >= 1000 and B == 8 and rank == 0:
-        from oracle import core as oracle
-        rng = np.random.default_rng(0)
-        rows = 2
-        a, b, c = [(rng.standard_normal((1, rows, K)) - 1.4).astype(np.float32) for _ in range(3)]
-        x = rng.standard_normal((rows, K, 1)).astype(np.float32)
-        uu = rng.random((T, rows))
-        t0 = time.perf_counter()
-        oracle.core_pass(a, b, c, uu, x, T)
-        dt = time.perf_counter() - t0
-        print(json.dumps({"K": K, "mode": "cpu oracle (C, 1 thread)", "particle_steps_per_s": rows * K * T / dt}), flush=True)
     del ring, arena, log_w, idx, ws
     torch.cuda.empty_cache()
 if world > 1:
