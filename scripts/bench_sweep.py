@@ -1,5 +1,6 @@
 """BASELINE config 5: resampling-bound sweep of the core step, K = 1e3 ... 1e6 particles per row, small
-batch (and the headline shape for comparison).  Prints one JSON line per (B, K, mode):
+batch (and the headline shape for comparison).  Prints one JSON line per (B, K, mode); `us_per_step` is the
+T-step loop replayed as one CUDA graph, `us_per_step_stepwise` the same launches issued one by one from Python:
 
     python scripts/bench_sweep.py [--steps 20] > profiles/r1_sweep.jsonl
 
@@ -59,23 +60,42 @@ for B, K in [(8, 1000), (64, 1000), (8, 10000), (64, 10000), (8, 100000), (64, 1
         for _ in range(3):
             run()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
-        if world > 1:
-            dist.barrier()
+
+        def timed(fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
             torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
+            t_ms = e0.elapsed_time(e1) / (reps * T)
+            if world > 1:
+                tt = torch.tensor([t_ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ms = float(tt.item())
+            return t_ms
+
+        ms_stepwise = timed(run)  # T launches issued from Python (ctypes), as infer() does
+        # the same T steps captured once as a CUDA graph: what the kernels cost without the host in the loop
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
             run()
-        e1.record()
+        torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (reps * T)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run()
+        graph.replay()
+        torch.cuda.synchronize()
+        ms = timed(graph.replay)
         gbs = 28.0 * B * K / (ms * 1e-3) / 1e9  # per GPU
         line = {"n_gpus": world, "B": B * world, "B_per_gpu": B, "K": K, "T": T, "mode": mode, "us_per_step": round(ms * 1e3, 2),
+                "us_per_step_stepwise": round(ms_stepwise * 1e3, 2),
                 "particle_steps_per_s": world * B * K / (ms * 1e-3), "algorithmic_GBps_per_gpu": round(gbs, 1),
                 "frac_of_measured_hbm": round(gbs / peak, 4), "path": "multi-CTA" if ws_bytes else "single-CTA",
                 "flags": int(flags.item())}
