@@ -13,7 +13,8 @@ scalar latent (D = 1), float32.  One bench "step" = one full pass of the hot pat
     e2e    aesmc_b200.inference.infer('smc', ...) -- the public API a user calls -- on the bootstrap-filter
            LGSSM, with the observations [T,B] in pinned HOST memory copied H2D inside the timed region and
            the log-evidence [B] copied back D2H; `e2e` uses a model of the fused family (evaluated inside
-           the step kernel), `e2e_eager` the same model written as plain torch callables
+           the step kernel), `e2e_eager` the same model written as plain torch callables, `e2e_eager_graph`
+           those callables with the whole infer() call replayed as a CUDA graph (inference.GraphedInfer)
 Rows are independent SMC problems, so ranks shard the batch axis with no data-path collective
 ("scaling": "weak": every rank processes B rows).
 """
@@ -209,7 +210,7 @@ def run_native(args):
     #   e2e        aesmc_b200.fused.ScalarLinearGaussianSSM -- infer() recognises it and evaluates the model
     #              inside the step kernel (one launch per time step)
     #   e2e_eager  plain torch callables (tests/models/lgssm.py) -- ~25 torch elementwise kernels per step
-    e2e = e2e_eager = None
+    e2e = e2e_eager = e2e_eager_graph = None
     if not args.no_e2e:
         from aesmc_b200 import fused
         ys = lgssm.simulate(T, B, seed=100 + rank)
@@ -258,6 +259,36 @@ def run_native(args):
                             "aesmc_b200.inference.infer('smc') on torch-eager user callables, "
                             "Distribution.set_default_validate_args(False)")
 
+        # the same torch-eager user model with the whole infer() call captured once as a CUDA graph
+        def measure_graphed(models, reps, label):
+            obs_host = torch.from_numpy(lgssm.simulate(T, B, seed=7 + rank)).pin_memory()
+            out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+            obs = obs_host.to(dev)
+            g = inference.GraphedInfer("smc", [obs[t] for t in range(T)], *models, K, return_log_marginal_likelihood=True,
+                                       return_latents=False, return_log_weight=False, resampling_mode=mode)
+
+            def one_pass():
+                dobs = obs_host.to(dev, non_blocking=True)
+                res = g([dobs[t] for t in range(T)])
+                out_host.copy_(res["log_marginal_likelihood"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            for _ in range(2):
+                one_pass()
+            barrier_sync(world)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                one_pass()
+            barrier_sync(world)
+            sec = max_over_ranks(time.perf_counter() - t0, world, dev)
+            assert bool(np.isfinite(out_host.numpy()).all())
+            return {"value": world * B * K * T / (sec / reps), "unit": UNIT, "h2d_bytes_per_step": obs_host.numel() * 4,
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": sec * 1e3 / reps, "steps": reps, "api": label}
+
+        e2e_eager_graph = measure_graphed(lgssm.bootstrap_filter(device=dev), reps,
+                                          "aesmc_b200.inference.GraphedInfer('smc') on the same torch-eager callables: "
+                                          "the whole infer() call replayed as one CUDA graph, uniforms drawn on the device")
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample ---------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -271,7 +302,7 @@ def run_native(args):
                                        % (B, K, T, D), "resampling_mode": mode, "parallelism": "batch rows sharded, dp%d" % world,
                            "l2": "inputs ring %d x %d MiB > 126 MB L2; no flush needed" % (RING, 3 * B * K * 4 >> 20)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(), "e2e": e2e,
-                "e2e_eager": e2e_eager, "gpu_launches": launches}
+                "e2e_eager": e2e_eager, "e2e_eager_graph": e2e_eager_graph, "gpu_launches": launches}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

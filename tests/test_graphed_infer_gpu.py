@@ -1,0 +1,69 @@
+"""inference.GraphedInfer: infer() on an arbitrary torch user model captured as one CUDA graph."""
+import numpy as np
+import pytest
+import torch
+
+from aesmc_b200 import inference
+from oracle import kalman
+from tests.models import lgssm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def no_distribution_validation():
+    # argument validation synchronises with the host (.all()), which a graph capture forbids
+    old = torch.distributions.Distribution._validate_args
+    torch.distributions.Distribution.set_default_validate_args(False)
+    yield
+    torch.distributions.Distribution.set_default_validate_args(old)
+
+
+def test_graph_replay_tracks_kalman_and_follows_new_observations(cuda):
+    T, B, K = 30, 8, 2048
+    ys = lgssm.simulate(T, B, seed=3)
+    ys2 = lgssm.simulate(T, B, seed=4)
+    obs = [torch.from_numpy(y).to(cuda) for y in ys]
+    torch.manual_seed(0)
+    g = inference.GraphedInfer("smc", obs, *lgssm.bootstrap_filter(device=cuda), K, return_log_marginal_likelihood=True,
+                               return_latents=False)
+    for data in (ys, ys2, ys):
+        res = g([torch.from_numpy(y).to(cuda) for y in data])
+        g.check()
+        exact = kalman.lgssm1d_log_evidence(data, 0.0, 1.0, 0.9, 1.0, 1.0, 0.25)
+        err = np.abs(res["log_marginal_likelihood"].cpu().numpy() - exact)
+        assert err.max() < 0.6, err
+        assert res["latents"] is None and res["log_weight"].shape == (B, K) and res["last_latent"].shape == (B, K)
+
+
+def test_seed_controls_a_replay_and_replays_differ(cuda):
+    T, B, K = 12, 4, 256
+    obs = [torch.randn(B, device=cuda) for _ in range(T)]
+    torch.manual_seed(0)
+    init, trans, emis, prop = lgssm.Initial(0.0, 1.0), lgssm.Transition(0.9, 1.0).to(cuda), lgssm.Emission(1.0, 0.5).to(cuda), \
+        lgssm.Proposal(0.8, 0.7).to(cuda)
+    g = inference.GraphedInfer("smc", obs, init, trans, emis, prop, K, return_log_marginal_likelihood=True,
+                               return_log_weights=True, return_ancestral_indices=True)
+    torch.manual_seed(5)
+    a = {k: (torch.stack(v) if isinstance(v, list) else v).clone() for k, v in g().items() if v is not None and k != "latents"}
+    b_lml = g()["log_marginal_likelihood"].clone()          # the generator moved on: a different draw
+    torch.manual_seed(5)
+    c = g()
+    assert not torch.equal(a["log_marginal_likelihood"], b_lml)
+    assert torch.equal(a["log_marginal_likelihood"], c["log_marginal_likelihood"])
+    assert torch.equal(a["ancestral_indices"], torch.stack(c["ancestral_indices"]))
+    assert len(c["latents"]) == T and c["ancestral_indices"][0].dtype == torch.int64
+
+
+def test_importance_sampling_and_argument_checks(cuda):
+    T, B, K = 6, 3, 512
+    obs = [torch.randn(B, device=cuda) for _ in range(T)]
+    g = inference.GraphedInfer("is", obs, *lgssm.bootstrap_filter(device=cuda), K, return_log_marginal_likelihood=True)
+    res = g()
+    assert torch.isfinite(res["log_marginal_likelihood"]).all() and len(res["latents"]) == T
+    with pytest.raises(ValueError):
+        g(obs[:-1])
+    with pytest.raises(ValueError):
+        inference.GraphedInfer("smc", obs, *lgssm.bootstrap_filter(device=cuda), K, uniforms=None)
+    with pytest.raises(ValueError):
+        inference.GraphedInfer("smc", [o.cpu() for o in obs], *lgssm.bootstrap_filter(device=cuda), K)
