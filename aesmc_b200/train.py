@@ -50,6 +50,77 @@ def train(dataloader, num_particles, algorithm, initial, transition, emission, p
                 callback(epoch_idx, epoch_iteration_idx, loss, initial, transition, emission, proposal)
 
 
+class GraphedTrainStep:
+    """One optimisation step -- get_loss() forward, backward, optimizer.step() -- captured once as a CUDA graph
+    and replayed per batch: at small and medium shapes a training step is bound by the hundreds of launches
+    torch issues for the user model and its autograd graph, not by the GPU.
+
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+        step = GraphedTrainStep(observations, num_particles, 'aesmc', initial, transition, emission, proposal, opt)
+        for batch in data:
+            loss = step(batch)            # 0-d CUDA tensor, overwritten by the next call
+
+    The constructor runs three ordinary (eager) steps on ``observations`` first -- they do train the model --
+    so that the optimizer state and autograd's lazily created buffers exist before the capture, as torch's
+    whole-network capture recipe requires.  Requirements: CUDA model and observations of fixed shapes, a
+    capturable optimizer (Adam-family: capturable=True), callables free of host synchronisation
+    (distributions with validate_args=False), a single process (no gradient all-reduce inside the graph).
+    Resampling uniforms come from torch's graph-safe generator on the device."""
+
+    def __init__(self, observations, num_particles, algorithm, initial, transition, emission, proposal, optimizer,
+                 resampling_mode=None, warmup_steps=3):
+        from . import inference
+        if distributed.world()[1] > 1:
+            raise NotImplementedError("GraphedTrainStep does not capture the gradient all-reduce; use train() under torch.distributed")
+        if optimizer.defaults.get("capturable") is False:
+            raise ValueError("construct the optimizer with capturable=True")
+        self._args = (num_particles, algorithm, initial, transition, emission, proposal)
+        self._mode = resampling_mode
+        self._optimizer = optimizer
+        self._inference = inference
+        self.observations = [inference._map_tensors(lambda v: v.detach().clone(), o) for o in observations]
+        probe = inference._first_tensor(self.observations[0])
+        if not probe.is_cuda:
+            raise ValueError("GraphedTrainStep needs CUDA observations")
+        self._dev, self._T, self._B = probe.device, len(self.observations), probe.size(0)
+        side = torch.cuda.Stream(device=self._dev)
+        side.wait_stream(torch.cuda.current_stream(self._dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup_steps):
+                self._step()
+        torch.cuda.current_stream(self._dev).wait_stream(side)
+        torch.cuda.synchronize(self._dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        num_particles, algorithm, initial, transition, emission, proposal = self._args
+        kwargs = {"check_finite": False, "_allow_fused": False, "resampling_mode": self._mode}
+        if algorithm == "aesmc" and self._T > 1:
+            kwargs["uniforms"] = torch.rand(self._T - 1, self._B, dtype=torch.float64, device=self._dev)
+        self._optimizer.zero_grad(set_to_none=True)
+        with self._inference._scalars_by_fill_kernel():
+            loss = losses.get_loss(self.observations, num_particles, algorithm, initial, transition, emission, proposal,
+                                   **kwargs)
+            loss.backward()
+        self._optimizer.step()
+        return loss.detach()
+
+    def __call__(self, observations=None):
+        if observations is not None:
+            if len(observations) != self._T:
+                raise ValueError("expected %d observations, got %d" % (self._T, len(observations)))
+            for dst, src in zip(self.observations, observations):
+                if isinstance(dst, dict):
+                    for name in dst:
+                        dst[name].copy_(src[name], non_blocking=True)
+                else:
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 class SyntheticDataset(torch.utils.data.Dataset):
     """Endless stream of observation sequences sampled from the generative model."""
 
