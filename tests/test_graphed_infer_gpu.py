@@ -95,3 +95,24 @@ def test_graphed_train_step_learns(cuda):
     with torch.no_grad():
         eager = float(losses.get_loss(obs, K, "aesmc", init, trans, emis, prop))
     assert abs(eager - last) < 0.5, (eager, last)
+
+
+def test_graphed_train_step_nonlinear_mlp_proposal(cuda):
+    """BASELINE config 4's model family (nonlinear SSM, MLP proposal with BATCH_EXPANDED / FULLY_EXPANDED
+    distributions) under the captured training step, both objectives."""
+    from aesmc_b200 import train
+    from tests.models import nonlinear
+    torch.manual_seed(0)
+    np.random.seed(0)
+    init = nonlinear.Initial(cuda)
+    true_trans, true_emis = nonlinear.Transition().to(cuda), nonlinear.Emission().to(cuda)
+    loader = train.get_synthetic_dataloader(init, true_trans, true_emis, num_timesteps=10, batch_size=32)
+    batch = next(iter(loader))
+    for algorithm in ("aesmc", "iwae"):
+        trans, emis = nonlinear.Transition(scale=2.0).to(cuda), nonlinear.Emission(mult=0.03).to(cuda)
+        prop = nonlinear.Proposal().to(cuda)
+        opt = torch.optim.Adam(train.get_chained_params(trans, emis, prop), lr=5e-3, capturable=True)
+        step = train.GraphedTrainStep(batch, 256, algorithm, init, trans, emis, prop, opt)
+        seen = [float(step(batch)) for _ in range(60)]
+        assert all(np.isfinite(seen)), seen[:5]
+        assert np.mean(seen[-5:]) < np.mean(seen[:5]), (algorithm, np.mean(seen[:5]), np.mean(seen[-5:]))
