@@ -25,7 +25,7 @@ __host__ __device__ inline int pairwise_max_nodes(int K) { return 2 * (K / 56 + 
 __device__ __forceinline__ int pad_chunk(int c) { return c + (c >> 3); }
 __device__ __forceinline__ int pad_elem(int k) { return k + ((k >> 5) << 2); }
 
-static __device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *nlevels, int K, int leaf_max = 128)
+static __device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *nlevels, int K)
 {
     nodes[0].start = 0; nodes[0].len = K; nodes[0].child = -1; nodes[0].val = 0.f;
     int begin = 0, end = 1, L = 0;
@@ -34,7 +34,7 @@ static __device__ void build_pairwise_tree(PwNode *nodes, int *lvl_start, int *n
         int cnt = end;
         for (int i = begin; i < end; ++i) {
             const int len = nodes[i].len, start = nodes[i].start;
-            if (len > leaf_max) {
+            if (len > 128) {
                 int n2 = len / 2;
                 n2 -= n2 % 8;
                 nodes[i].child = cnt;
