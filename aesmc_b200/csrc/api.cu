@@ -121,8 +121,8 @@ int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *nois
     REQUIRE(y && params_host && flags, fn);
     REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
     REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
-    REQUIRE((idx == nullptr) == (x_out == nullptr), fn);
-    REQUIRE(idx == nullptr || u != nullptr, fn);
+    REQUIRE(idx == nullptr || x_out != nullptr, fn); // ancestors may be dropped (idx NULL), the resampled latents not
+    REQUIRE(x_out == nullptr || u != nullptr, fn);
     if (!smc_step_lg_supported(K)) {
         set_error("%s: K=%lld not supported by the fused model kernel (64 <= K <= 16384, K %% 4 == 0)", fn, (long long)K);
         return AESMC_ERR_UNSUPPORTED;

@@ -135,7 +135,6 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
     keep_index = return_ancestral_indices or return_latents
     originals, log_weights, ancestors = [], [], []
     lses = torch.empty(T, B, dtype=torch.float32, device=dev)
-    scratch_idx = None if keep_index else torch.empty(B, K, dtype=torch.int32, device=dev)
     arena = [torch.empty(B, K, dtype=torch.float32, device=dev) for _ in range(2)]
     x_prev = None
     x_last = None
@@ -152,7 +151,7 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
         else:
             ut = np.random.uniform(size=[B, 1]) if uniforms is None else uniforms[t]  # inference.py:250
             u_dev = _ops.uniforms_to_device(ut, B, dev)
-            idx = torch.empty(B, K, dtype=torch.int32, device=dev) if keep_index else scratch_idx
+            idx = torch.empty(B, K, dtype=torch.int32, device=dev) if keep_index else None  # ancestors not stored
             x_out = arena[t & 1]
         nz = None if noise is None else noise[t].contiguous()
         _lib.call("aesmc_smc_step_lg_f32", _lib.ptr(x_prev), _lib.ptr(y), _lib.ptr(nz), _lib.ptr(q_off),
@@ -216,7 +215,6 @@ class GraphedFilter:
         self.flags = _ops.new_flags(dev)
         self.seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
         self._arena = [torch.empty(B, K, dtype=torch.float32, device=dev) for _ in range(2)]
-        self._idx = torch.empty(B, K, dtype=torch.int32, device=dev)
         self._q_off = None if model.prop is None else torch.empty(T, B, dtype=torch.float32, device=dev)
         self._params = model.kernel_params()
         self._mode = _ops.mode_code(resampling_mode)
@@ -254,7 +252,7 @@ class GraphedFilter:
                       None if self._inject else _lib.ptr(self.seed), t, B, K,
                       None if last else _lib.ptr(self.uniforms[t]), _lib.ptr(self.last_latent) if last else None,
                       _lib.ptr(self.log_weight) if last else None, _lib.ptr(self.lses[t]),
-                      None if last else _lib.ptr(self._idx), _lib.ptr(x_out), _lib.ptr(self.flags), self._mode)
+                      None, _lib.ptr(x_out), _lib.ptr(self.flags), self._mode)  # ancestors are not stored
             x_prev = x_out
         self.log_evidence.copy_((self.lses - math.log(K)).sum(dim=0))
 

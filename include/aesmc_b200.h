@@ -97,7 +97,8 @@ int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_
  *   seed_dev non-NULL: the key is read from device memory at run time, for CUDA-graph replays)
  *   q_off [B] per-row proposal offset or NULL (then the proposal's scalar offset)
  *   params_host: HOST pointer to 15 floats = (mult, off, scale, 2*scale^2, log scale) for t, e, q
- *   x_new, log_w: optional outputs (proposed latents, log-weights); idx/x_out both NULL to skip resampling
+ *   x_new, log_w: optional outputs (proposed latents, log-weights); x_out NULL skips resampling (last step);
+ *   idx may be NULL on its own when the ancestors are not wanted (filtering for the evidence only)
  */
 int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
                           const float *params_host, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
