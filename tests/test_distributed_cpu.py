@@ -58,8 +58,16 @@ def _worker(rank, world, port, B, out):
         per_row = (model(x).squeeze(-1) - y).detach()
         gathered = distributed.gather_rows(per_row, B)
         mean = distributed.global_mean(per_row, B)
+        # the captured training step refuses to run data-parallel (the NCCL all-reduce stays outside graphs)
+        from aesmc_b200 import train
+        try:
+            train.GraphedTrainStep([x], 4, "aesmc", None, None, None, None, torch.optim.SGD(model.parameters(), lr=0.1))
+            refused = False
+        except NotImplementedError:
+            refused = True
         if rank == 0:
-            torch.save({"grad_w": model.weight.grad, "grad_b": model.bias.grad, "rows": gathered, "mean": mean}, out)
+            torch.save({"grad_w": model.weight.grad, "grad_b": model.bias.grad, "rows": gathered, "mean": mean,
+                        "refused": refused}, out)
     finally:
         dist.destroy_process_group()
 
@@ -79,3 +87,4 @@ def test_two_rank_gradients_equal_single_process(tmp_path, B):
     rows = (model(x).squeeze(-1) - y).detach()
     torch.testing.assert_close(got["rows"], rows)            # global row order, ragged shards included
     torch.testing.assert_close(got["mean"], rows.mean())
+    assert got["refused"]
