@@ -14,6 +14,10 @@
 //     whether the whole block provably lies inside one binade ("pure") or may straddle a boundary
 //     ("mixed", ~10 blocks per row).
 //
+//   * a block whose weights are all below half an ulp of the running sum ("absorbed": zero padding,
+//     -inf log-weights, the plateaus of a collapsed weight vector) changes nothing: it is the identity
+//     in every binade and joins the pure run it follows.
+//
 // Runs of pure blocks are composed with a segmented shuffle scan, one thread walks the ~20 run/mixed
 // segments (O(1) per run, 16 real float additions per mixed block), and every thread then replays its
 // own block from its exact entry state.  Every block re-verifies that its partial sums stayed inside
