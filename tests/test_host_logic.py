@@ -178,3 +178,20 @@ def test_install_as_aesmc_alias():
         for k in [k for k in sys.modules if k == "aesmc" or k.startswith("aesmc.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_graph_wrappers_validate_arguments_before_touching_the_gpu():
+    """inference.GraphedInfer / train.GraphedTrainStep: the argument checks that need no device."""
+    from aesmc_b200 import inference, train
+    obs = [torch.zeros(3) for _ in range(4)]
+    with pytest.raises(ValueError, match="uniforms"):
+        inference.GraphedInfer("smc", obs, None, None, None, None, 8, uniforms=None)
+    with pytest.raises(ValueError, match="check_finite"):
+        inference.GraphedInfer("smc", obs, None, None, None, None, 8, check_finite=False)
+    with pytest.raises(ValueError, match="CUDA"):
+        inference.GraphedInfer("smc", obs, None, None, None, None, 8)
+    lin = torch.nn.Linear(1, 1)
+    with pytest.raises(ValueError, match="capturable"):
+        train.GraphedTrainStep(obs, 8, "aesmc", None, None, None, None, torch.optim.Adam(lin.parameters()))
+    with pytest.raises(ValueError, match="CUDA"):
+        train.GraphedTrainStep(obs, 8, "aesmc", None, None, None, None, torch.optim.SGD(lin.parameters(), lr=0.1))
