@@ -14,7 +14,8 @@ dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(0)
 for mode in ("exact", "fast"):
     for B, K, D in [(5, 4096, 1), (3, 1000, 1), (3, 2048, 3), (2, 1023, 1), (2, 30000, 1), (1, 70000, 2), (25, 33000, 1), (2, 40003, 1)]:
-        a, b, c = [torch.randn(B, K, device=dev, generator=gen) for _ in range(3)]
+        spread = 8.0 if K == 4096 else 1.0  # collapsed weights on one shape: absorbed blocks joining pure runs
+        a, b, c = [spread * torch.randn(B, K, device=dev, generator=gen) for _ in range(3)]
         x = torch.randn(B, K, D, device=dev, generator=gen) if D > 1 else torch.randn(B, K, device=dev, generator=gen)
         u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
         flags = _ops.new_flags(dev)
@@ -33,7 +34,10 @@ for D in (1, 2, 4, 10):
     B, K = 3, 1001 if D == 1 else 1000
     x = (torch.randn(B, K, D, device=dev, generator=gen) if D > 1 else torch.randn(B, K, device=dev, generator=gen)).requires_grad_()
     idx = torch.sort(torch.randint(0, K, (B, K), device=dev, generator=gen), dim=1).values
-    for ix, srt in ((idx.int(), True), (idx, True), (idx.flip(1).contiguous(), False)):
+    collapsed = idx.clone()
+    collapsed[0, 10:900] = collapsed[0, 10]     # a run of 890 children: the warp-cooperative completion
+    collapsed[1] = collapsed[1, 0]              # everything under one parent, long childless stretch after it
+    for ix, srt in ((idx.int(), True), (idx, True), (collapsed.int(), True), (idx.flip(1).contiguous(), False)):
         out = _ops.gather(x, ix, srt)
         out.backward(torch.ones_like(out))
 lw = torch.randn(5, 4096, device=dev, generator=gen)
