@@ -335,6 +335,31 @@ def normal_log_prob(distribution, value):
     return _NormalLogProb.apply(v_c, v_kind, l_c, l_kind, s_c, B, K)
 
 
+def independent_normal_log_prob(distribution, value):
+    """log-density of Independent(Normal(loc [B, K, D], scalar scale), 1) at value [B, K, D], summed over D, or
+    None when the operands do not fit.  The [B, K, D] tables are viewed as [B, K*D] and go through the
+    one-kernel Normal.log_prob above (bit-identical to torch's elementwise sequence); the sum over D is the
+    same torch reduction the generic path uses, so the result equals distribution.log_prob(value) bit for bit
+    -- one elementwise pass instead of six."""
+    if type(distribution) is not torch.distributions.Independent or distribution.reinterpreted_batch_ndims != 1:
+        return None
+    base = distribution.base_dist
+    if type(base) is not torch.distributions.Normal or value.dim() != 3:
+        return None
+    if not (value.is_cuda and value.dtype == torch.float32):
+        return None
+    B, K, D = value.shape
+    loc, scale = base.loc, base.scale
+    if loc.dtype != torch.float32 or scale.dtype != torch.float32 or tuple(loc.shape) != (B, K, D):
+        return None
+    if tuple(scale.shape) != (B, K, D) or any(scale.stride()) or scale.device != value.device:
+        return None  # only a scalar scale (expanded from one element)
+    if loc.device != value.device or not loc.is_contiguous():
+        return None
+    flat = _NormalLogProb.apply(value.contiguous().view(B, K * D), 0, loc.view(B, K * D), 0, scale[0, 0, 0], B, K * D)
+    return flat.view(B, K, D).sum(dim=2)
+
+
 def compose_index(prev, cur):
     B, K = prev.shape
     out = torch.empty_like(prev)

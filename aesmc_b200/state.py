@@ -104,6 +104,13 @@ def log_prob(distribution, value):
         fast = _ops.normal_log_prob(distribution, value)
         if fast is not None:
             return fast
+    if lead == 2 and have == 2 and value.is_cuda and type(distribution) is torch.distributions.Independent:
+        # Independent(Normal) with vector latents (BASELINE config 3): the elementwise part in one kernel
+        if getattr(distribution, "_validate_args", True):
+            distribution._validate_sample(value)
+        fast = _ops.independent_normal_log_prob(distribution, value)
+        if fast is not None:
+            return fast
     if lead == have or lead == have + 2:
         # The reference validates the sample unconditionally (state.py:142), which costs a host
         # synchronisation per call on CUDA tensors; here a distribution built with

@@ -286,3 +286,35 @@ def test_fused_normal_log_prob_bitwise_and_gradients(cuda):
     # operands outside the fast path fall back to torch
     d = Normal(rnd(B, K), rnd(B, K).abs() + 0.1)
     assert _ops.normal_log_prob(d, v) is None and torch.equal(state.log_prob(d, v), d.log_prob(v))
+
+
+def test_independent_normal_log_prob_fast_path(cuda):
+    """state.log_prob on Independent(Normal(loc [B,K,D], scalar scale), 1): equals torch's own log_prob bit for
+    bit (one elementwise kernel + the same reduction), gradients match torch autograd; operands outside the fast
+    path (per-dimension scales) still go through torch."""
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    B, K, D = 5, 300, 10
+    Normal, Independent = torch.distributions.Normal, torch.distributions.Independent
+    for scale in (0.7, torch.tensor(1.3, device=cuda)):
+        value = torch.randn(B, K, D, device=cuda, generator=gen).requires_grad_()
+        loc = torch.randn(B, K, D, device=cuda, generator=gen).requires_grad_()
+        sc = scale.clone().requires_grad_() if torch.is_tensor(scale) else scale
+        dist = Independent(Normal(loc, sc, validate_args=False), 1, validate_args=False)
+        assert _ops.independent_normal_log_prob(dist, value) is not None
+        got = state.log_prob(dist, value)
+        want = dist.log_prob(value)
+        assert got.shape == (B, K) and torch.equal(got, want)
+        cot = torch.randn(B, K, device=cuda, generator=gen)
+        leaves = [value, loc] + ([sc] if torch.is_tensor(scale) else [])
+        g_got = torch.autograd.grad(got, leaves, cot, retain_graph=True)
+        g_want = torch.autograd.grad(want, leaves, cot)
+        for a, b in zip(g_got, g_want):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-5)
+    # an expanded observation as value (stride 0 over particles) is accepted, per-dimension scales are not
+    y = torch.randn(B, D, device=cuda, generator=gen).unsqueeze(1).expand(B, K, D)
+    loc = torch.randn(B, K, D, device=cuda, generator=gen)
+    dist = Independent(Normal(loc, 0.5, validate_args=False), 1, validate_args=False)
+    assert torch.equal(state.log_prob(dist, y), dist.log_prob(y))
+    per_dim = Independent(Normal(loc, torch.rand(D, device=cuda, generator=gen) + 0.5, validate_args=False), 1, validate_args=False)
+    assert _ops.independent_normal_log_prob(per_dim, y) is None
+    assert torch.equal(state.log_prob(per_dim, y), per_dim.log_prob(y))
