@@ -110,8 +110,18 @@ def check(status):
     raise RuntimeError(msg)
 
 
+class DevicePointer(int):
+    """A raw device address that remembers which CUDA device it lives on, so that call() can launch on
+    that device's current stream whatever the process's current device is."""
+    device_index = -1
+
+
 def ptr(t):
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    p = DevicePointer(t.data_ptr())
+    p.device_index = t.device.index if t.is_cuda else -1
+    return p
 
 
 def stream():
@@ -119,6 +129,22 @@ def stream():
 
 
 def call(name, *args):
-    """Invoke an exported function on torch's current stream; maps error codes to exceptions."""
+    """Invoke an exported function; maps error codes to exceptions.
+
+    The kernels are enqueued on torch's current stream OF THE DEVICE THE POINTER ARGUMENTS LIVE ON (not of
+    the process's current device): tensors on cuda:1 while cuda:0 is current launch on cuda:1, ordered after
+    the torch ops that produced them.  All pointer arguments must share one device."""
     lib = load()
-    check(getattr(lib, name)(*args, stream()))
+    dev = -1
+    for a in args:
+        if type(a) is DevicePointer and a.device_index >= 0:
+            if dev < 0:
+                dev = a.device_index
+            elif a.device_index != dev:
+                raise ValueError("%s: pointer arguments live on different CUDA devices (cuda:%d and cuda:%d)"
+                                 % (name, dev, a.device_index))
+    if dev < 0 or dev == torch.cuda.current_device():
+        check(getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream))
+        return
+    with torch.cuda.device(dev):
+        check(getattr(lib, name)(*args, torch.cuda.current_stream(dev).cuda_stream))

@@ -393,3 +393,24 @@ def uniforms_to_device(u, B, dev):
     if u.dtype != torch.float64:
         u = u.double()
     return u.to(dev, non_blocking=True).contiguous()
+
+
+def uniforms_table_to_device(u, steps, B, dev):
+    """All per-step, per-row resampling uniforms as ONE contiguous float64 CUDA tensor [steps, B]: one
+    upload per infer() call instead of a pageable host-to-device copy per time step.  Accepts a numpy
+    array / tensor of shape [steps, B] or [steps, B, 1] (host or device), or a sequence of per-step rows."""
+    if steps == 0:
+        return torch.empty((0, B), dtype=torch.float64, device=dev)
+    if isinstance(u, (list, tuple)):
+        if all(torch.is_tensor(r) for r in u):
+            u = torch.stack([r.reshape(B) for r in u[:steps]])
+        else:
+            u = np.stack([np.asarray(r, dtype=np.float64).reshape(B) for r in u[:steps]])
+    if isinstance(u, np.ndarray):
+        u = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64))
+    if u.shape[0] < steps:
+        raise ValueError("uniforms: need %d rows of per-step uniforms, got %d" % (steps, u.shape[0]))
+    u = u[:steps].reshape(steps, B)
+    if u.dtype != torch.float64:
+        u = u.double()
+    return u.to(dev, non_blocking=True).contiguous()

@@ -64,6 +64,13 @@ class ScalarLinearGaussianSSM:
     def callables(self):
         return self.initial, self.transition, self.emission, self.proposal
 
+    def tensors(self):
+        base = [self.m0, self.s0, self.a, self.b, self.sx, self.c, self.d, self.sy]
+        return base + (list(self.prop.values()) if self.prop is not None else [])
+
+    def requires_grad(self):
+        return any(t.requires_grad for t in self.tensors())
+
     # ---- parameters for the fused kernel -------------------------------------------------------------
     def _affine(self, mult, off, scale):
         # (mult, off, scale, 2*var, log scale) computed with torch on the model's device, exactly as
@@ -111,6 +118,8 @@ def applicable(model, observations, num_particles):
         return False
     if first.dtype != torch.float32 or model.m0.device != first.device:
         return False
+    if torch.is_grad_enabled() and model.requires_grad():
+        return False  # infer_fused has no autograd: a trainable model takes the differentiable generic path
     return 64 <= num_particles <= 16384 and num_particles % 4 == 0
 
 
@@ -139,6 +148,10 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
     x_prev = None
     x_last = None
     log_w = None
+    u_all = None
+    if T > 1:  # inference.py:250: one np.random.uniform(size=[B, 1]) per step, here drawn and uploaded once
+        u_all = _ops.uniforms_table_to_device(np.random.uniform(size=[T - 1, B]) if uniforms is None else uniforms,
+                                              T - 1, B, dev)
     for t in range(T):
         last = t == T - 1
         y = observations[t].contiguous()
@@ -149,8 +162,7 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
         if last:
             u_dev = idx = x_out = None
         else:
-            ut = np.random.uniform(size=[B, 1]) if uniforms is None else uniforms[t]  # inference.py:250
-            u_dev = _ops.uniforms_to_device(ut, B, dev)
+            u_dev = u_all[t]
             idx = torch.empty(B, K, dtype=torch.int32, device=dev) if keep_index else None  # ancestors not stored
             x_out = arena[t & 1]
         nz = None if noise is None else noise[t].contiguous()

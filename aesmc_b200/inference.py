@@ -23,7 +23,11 @@ Extra keyword-only arguments (all optional, defaults reproduce the reference's b
     resampling_mode  'exact' | 'fast' (default: module setting, see set_resampling_mode)
     check_finite     read the device NaN/degeneracy flag once at the end and raise
                      FloatingPointError like inference.py:244-245 (default True; the only host
-                     synchronisation in infer)
+                     synchronisation in infer).  As in the reference, only weights that are actually
+                     RESAMPLED (SMC, steps 0..T-2) can raise; NaN / infinite weights in 'is' mode or
+                     at the last step propagate into the result.  Stricter than the reference in one
+                     case: a resampled row whose weights are all -inf (or contain +inf) raises too,
+                     where the reference silently emits out-of-range ancestor indices
 """
 import collections.abc
 import contextlib
@@ -123,11 +127,25 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
                                      return_ancestral_indices, uniforms=uniforms, resampling_mode=resampling_mode,
                                      check_finite=check_finite)
     keep_originals = return_original_latents or return_latents
+    grad_path = torch.is_grad_enabled()
+    # log-weights of every step are retained only when somebody can read them: the caller asked for
+    # them, or autograd saves them anyway; the last one serves return_log_weight
+    keep_log_weights = return_log_weights
+    keep_index = return_latents or return_ancestral_indices
+    u_all = None  # [T-1, B] float64 on the device: uploaded once, sliced per step
 
-    def draw_uniforms(t):
-        if uniforms is None:
-            return np.random.uniform(size=[B, 1])  # inference.py:250 -- numpy global RNG, one per row
-        return uniforms[t - 1]
+    def draw_uniforms(t, dev):
+        nonlocal u_all
+        if u_all is None:
+            if uniforms is None:
+                # inference.py:250 draws np.random.uniform(size=[B, 1]) once per step from numpy's global RNG;
+                # the T-1 draws are taken here in one call -- the same stream values in the same order (unless a
+                # user callable itself consumes numpy's global RNG between steps)
+                host = np.random.uniform(size=[T - 1, B])
+            else:
+                host = uniforms
+            u_all = _ops.uniforms_table_to_device(host, T - 1, B, dev)
+        return u_all[t - 1]
 
     # ---- t = 0 (inference.py:85-98) ------------------------------------------------------------
     q = proposal(time=0, observations=observations)
@@ -139,7 +157,11 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
     home = lq.device
     pending = tuple(_as_f32_device(v) for v in (lp, le, lq))  # log_w = (lp + le) - lq
     dev = pending[0].device
-    flags = _ops.new_flags(dev)
+    # flag word 0: steps whose weights are resampled -- the only place the reference raises
+    # (sample_ancestral_index, inference.py:244-245); word 1: everything else ('is' mode, the last step),
+    # where the reference lets NaN / infinite weights propagate into the result, and so does this
+    flag_words = torch.zeros(2, dtype=torch.int32, device=dev)
+    flags, quiet_flags = flag_words[0:1], flag_words[1:2]
     originals = [latent] if keep_originals else None
     log_weights, lses, ancestors = [], [], []
     total = None  # running sum of log-weights in 'is' mode
@@ -152,30 +174,44 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
         if smc:
             newest = history[-1]
             fuse = resample_u is not None and _fusable(newest)
-            u_dev = None if resample_u is None else _ops.uniforms_to_device(resample_u, B, dev)
             x = newest.contiguous() if fuse else None
-            log_w, lse, idx, x_res = _ops.smc_step(a, b, c, u_dev, x, flags, resampling_mode,
-                                                   resample=resample_u is not None)
-            log_weights.append(log_w)
+            log_w, lse, idx, x_res = _ops.smc_step(a, b, c, resample_u, x,
+                                                   flags if resample_u is not None else quiet_flags,
+                                                   resampling_mode, resample=resample_u is not None)
+            if keep_log_weights:
+                log_weights.append(log_w)
+            else:
+                log_weights[:] = [log_w]
             lses.append(lse)
             return idx, x_res
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (a, b, c)):
-            log_w, _, _, _ = _ops.smc_step(a, b, c, None, None, flags, resampling_mode, resample=False)
-            total = log_w if total is None else total + log_w  # inference.py:156 (sequential over t)
+        if grad_path and any(t.requires_grad for t in (a, b, c)):
+            log_w, _, _, _ = _ops.smc_step(a, b, c, None, None, quiet_flags, resampling_mode, resample=False)
+            # inference.py:156 (sequential over t).  `total` is never an alias of a per-step tensor: a
+            # later step without gradients may accumulate into it in place
+            total = log_w + 0 if total is None else total + log_w
         else:  # one pass: log_w = (a + b) - c and total += log_w (aesmc_is_accumulate_f32)
-            log_w = torch.empty_like(a)
+            log_w = torch.empty_like(a) if keep_log_weights else None
             first = total is None
             if first:
                 total = torch.empty_like(a)
+            elif total.requires_grad:  # earlier steps carried gradients: stay out of place
+                term = torch.empty_like(a)
+                _ops.is_accumulate(a, b, c, term, None, True)
+                total = total + term
+                if keep_log_weights:
+                    log_weights.append(term)
+                return None, None
             _ops.is_accumulate(a, b, c, total, log_w, first)
-        log_weights.append(log_w)
+        if keep_log_weights:
+            log_weights.append(log_w)
         return None, None
 
     # ---- t = 1 .. T-1 (inference.py:99-126) -------------------------------------------------
     for t in range(1, T):
         if smc:
-            idx, x_res = close_step(draw_uniforms(t))
-            ancestors.append(idx)
+            idx, x_res = close_step(draw_uniforms(t, dev))
+            if keep_index:
+                ancestors.append(idx)
             previous = ResampledHistory(history, idx, x_res, home)
         else:
             close_step(None)
@@ -214,7 +250,7 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
             result["ancestral_indices"] = [back(_ops.widen_index(i)) for i in ancestors]
     else:
         if return_log_marginal_likelihood:
-            result["log_marginal_likelihood"] = back(_ops.logsumexp_rows(total, flags) - _pymath.log(K))
+            result["log_marginal_likelihood"] = back(_ops.logsumexp_rows(total, quiet_flags) - _pymath.log(K))
         if return_latents:
             result["latents"] = originals
         if return_original_latents:
@@ -327,9 +363,12 @@ class GraphedInfer:
                 raise FloatingPointError("log_weight contains nan element(s)")
 
 
-def _trace_genealogy(latents, ancestors32, home):
+def _trace_genealogy(latents, ancestors32, home, sorted_rows=True):
     """Back-trace with int32 device indices: latents[t] re-indexed by the composed ancestry of the
-    final particles (inference.py:196-231)."""
+    final particles (inference.py:196-231).  sorted_rows: every row of every index table is
+    non-decreasing (true for the systematic-resampling kernel's output, and then for compositions of
+    such tables); selects the deterministic sorted gather backward.  Indices of unknown origin must pass
+    False: the sorted backward is wrong for unsorted rows."""
     T = len(latents)
     probe = _first_tensor(latents[0])
     B, K = probe.shape[:2]
@@ -341,7 +380,7 @@ def _trace_genealogy(latents, ancestors32, home):
             out[t] = _map_tensors(lambda v: v.clone(), latents[t])
         else:
             def gather(v, cursor=cursor):
-                r = _ops.gather(_ops.to_device(v), cursor, sorted_rows=True)
+                r = _ops.gather(_ops.to_device(v), cursor, sorted_rows=sorted_rows)
                 return r if v.is_cuda else r.to(home)
             out[t] = _map_tensors(gather, latents[t])
         if t > 0:
@@ -363,7 +402,9 @@ def get_resampled_latents(latents, ancestral_indices):
     for a in ancestral_indices:
         a = _ops.to_device(a)
         idx32.append(a if a.dtype == torch.int32 else _ops.narrow_index(a.long().contiguous()))
-    return _trace_genealogy(list(latents), idx32, home)
+    # user-supplied indices may come from any resampler (multinomial, permuted ...): the gather backward
+    # must not assume sorted rows (the reference's torch.gather backward is correct for any index)
+    return _trace_genealogy(list(latents), idx32, home, sorted_rows=False)
 
 
 def sample_ancestral_index(log_weight, *, uniforms=None, resampling_mode=None):

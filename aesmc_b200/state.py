@@ -128,14 +128,17 @@ def log_prob(distribution, value):
     return lp.reshape(value.size(0), value.size(1), -1).sum(dim=2)
 
 
-def resample(value, ancestral_index):
+def resample(value, ancestral_index, *, check_range=True):
     """Ancestral gather without side effects: out[b, k, ...] = value[b, ancestral_index[b, k], ...].
 
     value: tensor [batch_size, num_particles, ...] or dict thereof; ancestral_index: integer tensor
     [batch_size, num_particles] (arbitrary order).  Runs aesmc_gather_bytes on the GPU; CPU inputs are
-    staged through the device and returned on the CPU."""
+    staged through the device and returned on the CPU.  An index outside [0, num_particles) raises
+    IndexError (torch.gather raises on the CPU and device-asserts on CUDA); the check reads a device flag
+    word, one host synchronisation -- callers inside a CUDA-graph capture or a latency-critical loop pass
+    check_range=False (out-of-range indices are then clamped)."""
     if isinstance(value, dict):
-        return {name: resample(v, ancestral_index) for name, v in value.items()}
+        return {name: resample(v, ancestral_index, check_range=check_range) for name, v in value.items()}
     if not torch.is_tensor(value):
         raise AttributeError("value must be a dict or a torch.Tensor. Got: {}".format(value))
     assert ancestral_index.size() == value.size()[:2]
@@ -146,8 +149,9 @@ def resample(value, ancestral_index):
         idx = idx.long()
     flags = _ops.new_flags(v.device)
     out = _ops.gather(v, idx, sorted_rows=False, flags=flags)
-    if not value.is_cuda:
+    if check_range and not torch.cuda.is_current_stream_capturing():
         _ops.raise_on_flags(flags)
+    if not value.is_cuda:
         out = out.to(home)
     return out
 

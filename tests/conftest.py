@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the reference's own unittest files, vendored as fixtures: run only through
+# tests/test_reference_unittests_gpu.py (with `aesmc` aliased to this package), never collected directly
+collect_ignore_glob = ["golden/ref_tests/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

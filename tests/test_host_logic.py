@@ -195,3 +195,20 @@ def test_graph_wrappers_validate_arguments_before_touching_the_gpu():
         train.GraphedTrainStep(obs, 8, "aesmc", None, None, None, None, torch.optim.Adam(lin.parameters()))
     with pytest.raises(ValueError, match="CUDA"):
         train.GraphedTrainStep(obs, 8, "aesmc", None, None, None, None, torch.optim.SGD(lin.parameters(), lr=0.1))
+
+
+def test_vendored_reference_tests_are_unmodified():
+    """tests/golden/ref_tests/test/ must stay byte-identical to the reference's test/ package (checked where
+    the reference checkout exists: the build container, not the GPU box)."""
+    import filecmp
+    import glob
+    import os
+    import pytest
+    ref = "/root/reference/test"
+    if not os.path.isdir(ref):
+        pytest.skip("no reference checkout here")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tests", "test")
+    files = sorted(glob.glob(os.path.join(ref, "**", "*.py"), recursive=True))
+    assert len(files) >= 8
+    for f in files:
+        assert filecmp.cmp(f, os.path.join(here, os.path.relpath(f, ref)), shallow=False), f
