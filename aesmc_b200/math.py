@@ -29,6 +29,9 @@ def _normalise(values, dim, exponentiate):
     t = torch.from_numpy(np.ascontiguousarray(values)) if as_numpy else values
     if t.dim() == 0:
         raise ValueError("values must have at least one dimension")
+    if not t.is_floating_point():
+        # integer input (the reference's tests pass np.array([1, 2, 3])): scipy / numpy promote to float64
+        t = t.double()
     home, dtype = t.device, t.dtype
     work = _ops.to_device(t.detach() if as_numpy else t)
     flat, restore = _rows_view(work, dim)

@@ -289,6 +289,19 @@ def run_native(args):
                                           "aesmc_b200.inference.GraphedInfer('smc') on the same torch-eager callables: "
                                           "the whole infer() call replayed as one CUDA graph, uniforms drawn on the device")
 
+    # ---- extra legs: parity counts, strong scaling, config-5 sweep, config-4 training ----
+    extras = {}
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        ctx = {"rank": rank, "world": world, "dev": dev, "mode": mode, "K": K, "T": T, "B": B}
+        for name, fn in (("parity", leg_parity), ("strong", leg_strong), ("sweep_c5", leg_sweep_c5),
+                         ("train_c4", leg_train_c4)):
+            try:
+                extras[name] = fn(ctx, ring, arena, u, value, ms_per_step)
+            except Exception as exc:  # an extra leg must never take the headline line down with it
+                extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample ---------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -303,9 +316,256 @@ def run_native(args):
                            "l2": "inputs ring %d x %d MiB > 126 MB L2; no flush needed" % (RING, 3 * B * K * 4 >> 20)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(), "e2e": e2e,
                 "e2e_eager": e2e_eager, "e2e_eager_graph": e2e_eager_graph, "gpu_launches": launches}
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# extra legs: each returns a small dict that becomes a key of the JSON line (all ranks must call them:
+# the multi-rank ones contain collectives; rank 0's dict is the one printed)
+# --------------------------------------------------------------------------------------------------
+def _event_time_ms(fn, reps, world, dev):
+    """fn() x reps between two CUDA events on the current stream, barrier + sync either side, max over ranks."""
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1) / 1e3, world, dev) * 1e3 / reps
+
+
+def _graphed(fn, dev):
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    return g
+
+
+def leg_parity(ctx, ring, arena, u, value, ms_per_step, rows=64):
+    """the GPU path against the CPU oracle (oracle/smc_oracle.c, the reference's
+    arithmetic: inference.py:250-264, math.py:6-51) on `rows` full-size rows of this very workload --
+    ancestor-index mismatches, max |delta idx|, and the relative error of log-weights, per-step lse and the
+    log-evidence.  Rank 0 only (the oracle is the checker here, never the thing measured)."""
+    if ctx["rank"] != 0:
+        return None
+    from aesmc_b200 import _lib, _ops
+    from oracle import core as oracle
+    dev, K, T, mode = ctx["dev"], ctx["K"], ctx["T"], ctx["mode"]
+    R = min(rows, ctx["B"])
+    code = _ops.mode_code(mode)
+    sub = [[t[:R].contiguous() for t in trio] for trio in ring]
+    x = [arena[0][:R].clone(), torch.empty(R, K, device=dev)]
+    x0 = x[0].cpu().numpy().copy()
+    uu = u[:, :R].contiguous()
+    lw = torch.empty(T, R, K, device=dev)
+    idx = torch.empty(max(T - 1, 1), R, K, dtype=torch.int32, device=dev)
+    lse = torch.empty(T, R, device=dev)
+    flags = _ops.new_flags(dev)
+    for t in range(T):
+        a, b, c = sub[t % RING]
+        last = t == T - 1
+        _lib.call("aesmc_smc_step_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), None if last else _lib.ptr(uu[t]), R, K,
+                  _lib.ptr(lw[t]), _lib.ptr(lse[t]), None if last else _lib.ptr(idx[t]),
+                  None if last else _lib.ptr(x[t & 1]), None if last else _lib.ptr(x[(t + 1) & 1]), 1, _lib.ptr(flags),
+                  code)
+    torch.cuda.synchronize()
+    g_lw, g_idx, g_lse = lw.cpu().numpy(), idx.cpu().numpy(), lse.cpu().numpy()
+    g_x = x[(T - 1) & 1].cpu().numpy()
+    h = [[t.cpu().numpy() for t in trio] for trio in sub]
+    hu = uu.cpu().numpy()
+    t0 = time.perf_counter()
+    mism = near = n_idx = 0
+    max_d = 0
+    lw_bits_differ = 0
+    lse_rel = lw_rel = 0.0
+    xr = x0
+    ev_ref = np.zeros(R, np.float64)
+    for t in range(T):
+        a, b, c = h[t % RING]
+        lw_ref = oracle.log_weight(a, b, c)
+        lw_bits_differ += int((lw_ref.view(np.int32) != g_lw[t].view(np.int32)).sum())
+        lw_rel = max(lw_rel, float(np.max(np.abs(lw_ref - g_lw[t]) / np.maximum(np.abs(lw_ref), 1e-30))))
+        if t < T - 1:
+            idx_ref, st, lse_ref, _, cdf_ref = oracle.sample_ancestral_index(lw_ref, hu[t], return_parts=True)
+            assert st == 0
+            d = idx_ref.astype(np.int64) - g_idx[t].astype(np.int64)
+            bad = np.nonzero(d)
+            n_idx += d.size
+            mism += len(bad[0])
+            if len(bad[0]):
+                max_d = max(max_d, int(np.abs(d).max()))
+                # a disagreement is "at a boundary" when the position (u + k)/K lies within 1 ulp of the
+                # CDF entry that separates the two candidate ancestors (north_star's allowance)
+                cn = (cdf_ref / cdf_ref[:, -1:]).astype(np.float32)
+                for r_, k_ in zip(*bad):
+                    pos = (hu[t][r_] + k_) / K
+                    j = min(int(idx_ref[r_, k_]), int(g_idx[t][r_, k_]))
+                    edge = np.float32(cn[r_, j])
+                    near += int(abs(pos - float(edge)) <= float(np.spacing(edge)))
+            xr = oracle.resample(xr.reshape(R, K, 1), idx_ref).reshape(R, K)
+        else:
+            lse_ref = oracle.logsumexp_rows(lw_ref)
+        lse_rel = max(lse_rel, float(np.max(np.abs(lse_ref - g_lse[t]) / np.maximum(np.abs(lse_ref), 1e-30))))
+        ev_ref += lse_ref.astype(np.float64) - math.log(K)
+    ev_gpu = (g_lse.astype(np.float64) - math.log(K)).sum(axis=0)
+    return {"against": "oracle/smc_oracle.c (CPU restatement of inference.py:250-264, math.py:6-51), same inputs and uniforms",
+            "rows": R, "K": K, "T": T, "mode": mode, "indices_compared": n_idx, "index_mismatches": mism,
+            "mismatches_within_1ulp_of_cdf_boundary": near, "max_abs_idx_diff": max_d,
+            "log_w_bits_differing": lw_bits_differ, "log_w_max_rel_err": lw_rel, "lse_max_rel_err": lse_rel,
+            "log_evidence_max_rel_err": float(np.max(np.abs(ev_gpu - ev_ref) / np.maximum(np.abs(ev_ref), 1e-30))),
+            "resampled_latent_equal": bool(np.array_equal(g_x, xr)) if T > 1 else None,
+            "flags": int(flags.item()), "tolerance": "indices bit-exact (exact mode); log-weights / log-evidence 1e-5 relative",
+            "oracle_seconds": round(time.perf_counter() - t0, 2)}
+
+
+def leg_strong(ctx, ring, arena, u, value, ms_per_step):
+    """Strong scaling of BASELINE config 2: B = 4096 rows IN TOTAL, 4096 / N per rank (at 8 GPUs 512 rows per
+    rank: less than one wave of the 592-CTA grid).  The T launches + the evidence reduction are replayed as
+    one CUDA graph per rank (at 512 rows a launch is ~25 us: issuing from Python would time the host)."""
+    from aesmc_b200 import _lib, _ops
+    world, dev, K, T, mode = ctx["world"], ctx["dev"], ctx["K"], ctx["T"], ctx["mode"]
+    total = ctx["B"]
+    if world == 1:
+        return {"value": value, "unit": UNIT, "rows_total": total, "rows_per_rank": total, "ms_per_step": ms_per_step,
+                "note": "N = 1: identical to the headline `value`"}
+    Bs = total // world
+    code = _ops.mode_code(mode)
+    sub = [[t[:Bs] for t in trio] for trio in ring]  # leading rows of a row-major table: contiguous
+    x = [arena[0][:Bs], arena[1][:Bs]]
+    lw = torch.empty(T, Bs, K, device=dev)
+    idx = torch.empty(T, Bs, K, dtype=torch.int32, device=dev)
+    lse = torch.empty(T, Bs, device=dev)
+    lml = torch.empty(Bs, device=dev)
+    flags = _ops.new_flags(dev)
+
+    def one_pass():
+        for t in range(T):
+            a, b, c = sub[t % RING]
+            last = t == T - 1
+            _lib.call("aesmc_smc_step_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), None if last else _lib.ptr(u[t]), Bs, K,
+                      _lib.ptr(lw[t]), _lib.ptr(lse[t]), None if last else _lib.ptr(idx[t]),
+                      None if last else _lib.ptr(x[t & 1]), None if last else _lib.ptr(x[(t + 1) & 1]), 1,
+                      _lib.ptr(flags), code)
+        lml.copy_((lse - math.log(K)).sum(dim=0))
+
+    for _ in range(2):
+        one_pass()
+    ms_stepwise = _event_time_ms(one_pass, 5, world, dev)
+    g = _graphed(one_pass, dev)
+    ms = _event_time_ms(g.replay, 10, world, dev)
+    assert int(flags.item()) == 0
+    return {"value": Bs * world * K * T / (ms * 1e-3), "unit": UNIT, "rows_total": Bs * world, "rows_per_rank": Bs,
+            "ms_per_step": ms, "ms_per_step_launched_from_python": ms_stepwise, "scaling": "strong",
+            "note": "one CUDA-graph replay per rank per pass; device time, max over ranks; no data-path collective"}
+
+
+def leg_sweep_c5(ctx, ring, arena, u, value, ms_per_step):
+    """BASELINE config 5 (resampling-bound, multi-CTA path): K = 1e5 and 1e6 particles per row, B = 64 rows IN
+    TOTAL (64 / N per rank), T = 20 steps replayed as one CUDA graph; exact and fast modes."""
+    from aesmc_b200 import _lib, _ops
+    world, dev = ctx["world"], ctx["dev"]
+    peak, _ = load_peaks()
+    Bs, T = max(64 // world, 1), 20
+    out = []
+    for K in (100000, 1000000):
+        gen = torch.Generator(device=dev).manual_seed(5 + ctx["rank"])
+        trio = [[torch.randn(Bs, K, device=dev, generator=gen) - 1.4 for _ in range(3)] for _ in range(2)]
+        x = [torch.randn(Bs, K, device=dev, generator=gen), torch.empty(Bs, K, device=dev)]
+        uu = torch.rand(T, Bs, dtype=torch.float64, device=dev, generator=gen)
+        lw, lse = torch.empty(Bs, K, device=dev), torch.empty(Bs, device=dev)
+        idx = torch.empty(Bs, K, dtype=torch.int32, device=dev)
+        flags = _ops.new_flags(dev)
+        ws_bytes = int(_lib.load().aesmc_smc_step_workspace_bytes(Bs, K))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        for mode in ("exact", "fast"):
+            code = _ops.mode_code(mode)
+
+            def run():
+                for t in range(T):
+                    a, b, c = trio[t & 1]
+                    _lib.call("aesmc_smc_step_ws_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(uu[t]), Bs, K,
+                              _lib.ptr(lw), _lib.ptr(lse), _lib.ptr(idx), _lib.ptr(x[t & 1]), _lib.ptr(x[(t + 1) & 1]), 1,
+                              _lib.ptr(flags), code, _lib.ptr(ws) if ws_bytes else None, ws_bytes)
+
+            for _ in range(2):
+                run()
+            g = _graphed(run, dev)
+            ms = _event_time_ms(g.replay, 3, world, dev) / T
+            gbs = 28.0 * Bs * K / (ms * 1e-3) / 1e9
+            out.append({"K": K, "rows_total": Bs * world, "rows_per_rank": Bs, "mode": mode, "us_per_step": round(ms * 1e3, 2),
+                        "value": Bs * world * K / (ms * 1e-3), "unit": UNIT, "algorithmic_GBps_per_gpu": round(gbs, 1),
+                        "frac_of_measured_hbm": round(gbs / peak, 4), "flags": int(flags.item())})
+        del trio, x, lw, idx, ws
+        torch.cuda.empty_cache()
+    return out
+
+
+def leg_train_c4(ctx, ring, arena, u, value, ms_per_step):
+    """BASELINE config 4: AESMC training ('aesmc' = SMC ELBO, losses.py:5-65) of the nonlinear state-space
+    model with an MLP proposal, batch rows sharded over the ranks, the flattened-gradient NCCL all-reduce of
+    train.py:36->37 INSIDE the timed optimiser step; its own duration is timed with CUDA events."""
+    from aesmc_b200 import distributed, losses, train
+    from tests.models import nonlinear
+    world, dev, rank = ctx["world"], ctx["dev"], ctx["rank"]
+    Bl, K, T = 512, 1024, 20
+    torch.distributions.Distribution.set_default_validate_args(False)
+    torch.manual_seed(1000 + rank)
+    np.random.seed(1000 + rank)
+    init = nonlinear.Initial(dev)
+    loader = train.get_synthetic_dataloader(init, nonlinear.Transition().to(dev), nonlinear.Emission().to(dev), T, Bl)
+    batch = next(iter(loader))
+    torch.manual_seed(0)  # identical replicas
+    trans, emis, prop = nonlinear.Transition(scale=2.0).to(dev), nonlinear.Emission(mult=0.03).to(dev), nonlinear.Proposal().to(dev)
+    params = list(train.get_chained_params(trans, emis, prop))
+    opt = torch.optim.Adam(params, lr=1e-3)
+    ar_events = []
+
+    def step(record=False):
+        opt.zero_grad()
+        loss = losses.get_loss(batch, K, "aesmc", init, trans, emis, prop)
+        loss.backward()
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            distributed.all_reduce_gradients(params, Bl, Bl * world)
+            e1.record()
+            if record:
+                ar_events.append((e0, e1))
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    reps = 8
+    ms = _event_time_ms(lambda: step(True), reps, world, dev)
+    ar_us = None
+    if ar_events:
+        ar_us = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events) * 1e-3, world, dev) * 1e6
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    in_sync = True
+    if world > 1:
+        ref = flat.clone()
+        torch.distributed.broadcast(ref, src=0)
+        ok = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        in_sync = bool(ok.item())
+    return {"model": "nonlinear SSM + MLP proposal (hidden 32), get_loss('aesmc') forward + backward + all-reduce + Adam, torch-eager",
+            "rows_per_rank": Bl, "rows_total": Bl * world, "K": K, "T": T, "ms_per_optimizer_step": ms,
+            "allreduce_us": ar_us, "allreduce_floats": int(flat.numel()), "replicas_in_sync": in_sync,
+            "value": Bl * world * K * T / (ms * 1e-3), "unit": UNIT, "scaling": "weak"}
+
 
 
 def time_oracle_core(K, T, D, rows):
@@ -380,6 +640,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / strong / sweep_c5 / train_c4 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
