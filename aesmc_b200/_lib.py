@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaesmc_b200.so")
+# AESMC_B200_LIB: measure an alternative build of the same library (kernel experiments); default: the in-tree build
+LIB_PATH = os.environ.get("AESMC_B200_LIB") or os.path.join(_HERE, "libaesmc_b200.so")
 
 OK, ERR_BAD_ARG, ERR_LAUNCH, ERR_UNSUPPORTED = 0, 1, 2, 3
 FLAG_NAN, FLAG_DEGENERATE, FLAG_INDEX_RANGE = 1, 2, 4

@@ -80,36 +80,38 @@ __global__ void logsumexp_rows_kernel(const T *__restrict__ lw, int B, int K, T 
     }
 }
 
-// out = lw - lse (exponentiate=0) or exp(lw - lse)
+// out = lw - lse (exponentiate=0) or exp(lw - lse) = softmax (math.py:6-51).  The normaliser and the final
+// exp / subtraction are evaluated in float64 and rounded once, so every output is within half a float32 ulp
+// (plus ~1e-16) of the exact value: the reference's own tests compare against exact float64 values at
+// rtol = 1e-7 (test_math.py:119-126), which a float32 lse (its rounding alone moves exp(lw - lse) by up to
+// |lse| * 6e-8 relative) only meets by luck.  Off the hot path (the step kernel normalises its own weights).
 __global__ void lognormexp_kernel(const float *__restrict__ lw, int B, int K, float *__restrict__ out, int exponentiate)
 {
     __shared__ float scratch[32];
+    __shared__ double scratch_d[32];
     for (int row = blockIdx.x; row < B; row += gridDim.x) {
         const float *r = lw + (size_t)row * K;
         float *o = out + (size_t)row * K;
         int bad;
         const float m = row_max(r, K, scratch, &bad);
-        float lse;
+        double lse;
         if (bad) lse = NAN;
         else if (!(fabsf(m) < INFINITY)) lse = m;
         else {
-            float s = 0.f;
-            for_each_in_row(r, K, [&](float v) { s += expf(v - m); });
-            s = block_allreduce(s, 0.f, OpSumF(), scratch);
-            lse = m + logf(s);
+            double s = 0.0;
+            for_each_in_row(r, K, [&](float v) { s += exp((double)v - (double)m); });
+            s = block_allreduce(s, 0.0, OpSumD(), scratch_d);
+            lse = (double)m + log(s);
         }
+        auto f = [&](float v) { const double d = (double)v - lse; return (float)(exponentiate ? exp(d) : d); };
         if ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
             for (int c = threadIdx.x; c < (K >> 2); c += blockDim.x) {
                 float4 v = reinterpret_cast<const float4 *>(r)[c];
-                v.x -= lse; v.y -= lse; v.z -= lse; v.w -= lse;
-                if (exponentiate) { v.x = expf(v.x); v.y = expf(v.y); v.z = expf(v.z); v.w = expf(v.w); }
+                v.x = f(v.x); v.y = f(v.y); v.z = f(v.z); v.w = f(v.w);
                 reinterpret_cast<float4 *>(o)[c] = v;
             }
         } else {
-            for (int k = threadIdx.x; k < K; k += blockDim.x) {
-                const float d = r[k] - lse;
-                o[k] = exponentiate ? expf(d) : d;
-            }
+            for (int k = threadIdx.x; k < K; k += blockDim.x) o[k] = f(r[k]);
         }
     }
 }

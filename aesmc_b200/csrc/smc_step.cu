@@ -303,6 +303,9 @@ int64_t smc_step_large_workspace_bytes(int64_t B, int64_t K);
 int launch_smc_step_large(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
                           int32_t *, const float *, float *, int64_t, int32_t *, int, void *, int64_t, cudaStream_t);
 bool smc_step_reg_supported(int64_t K, bool vec);
+bool smc_step_x_supported(int64_t K, int mode, const void *idx, const void *x_in, int64_t D);
+int launch_smc_step_x(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
+                      int32_t *, const float *, float *, int32_t *, cudaStream_t);
 int launch_smc_step_reg(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
                         int32_t *, const float *, float *, int64_t, int32_t *, int, cudaStream_t);
 
@@ -357,8 +360,11 @@ int launch_smc_step(const float *a, const float *b, const float *c, const double
                                reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(log_w);
         p.vec = ((K & 3) == 0) && ((bits & 15) == 0);
     }
-    if (stage == 0 && smc_step_reg_supported(K, p.vec != 0) &&
-        ((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(idx)) & 15) == 0)
+    const bool aligned16 = p.vec && ((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x_out) |
+                                      reinterpret_cast<uintptr_t>(idx)) & 15) == 0;
+    if (stage == 0 && aligned16 && smc_step_x_supported(K, mode, idx, x_in, D))
+        return launch_smc_step_x(a, b, c, u, B, K, log_w, lse, idx, x_in, x_out, flags, stream);
+    if (stage == 0 && smc_step_reg_supported(K, p.vec != 0) && aligned16)
         return launch_smc_step_reg(a, b, c, u, B, K, log_w, lse, idx, x_in, x_out, D, flags, mode, stream);
     const size_t smem = step_smem_bytes((int)K, exact);
     // long rows the register-blocked kernel did not take: the multi-CTA path is 3-4x faster than the

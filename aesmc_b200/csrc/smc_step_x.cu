@@ -1,0 +1,688 @@
+// smc_step_x.cu -- second-generation EXACT-mode fused SMC step for the common row shapes
+// (K = 16 * NT particles, NT = 64 ... 1024 threads, i.e. K = 1024, 2048, 4096, 8192, 16384; scalar latent).
+//
+// Same contract and the same bits as smc_step_reg.cu's exact instance -- log_w = (a + b) - c, scipy's
+// logsumexp in numpy's pairwise order, np.cumsum's sequential float32 chain evaluated in parallel
+// (see exact_scan.cuh for the theory), IEEE cdf / total, the float64 position comparison, the ancestral
+// gather (inference.py:97-104,125-126,130,234-269; state.py:158-183) -- reorganised around what the
+// round-1 profile showed (issue-bound at 49 % utilisation, 15 CTA barriers per row, 16.6 % of the stall
+// samples behind the one-thread segment walker):
+//
+//   * the CTA size is a template parameter: K, the chunk strides and every padded shared-memory
+//     address are compile-time constants (the generic kernel spends ~5 % of its instructions on them);
+//   * HBM I/O is striped PER WARP (warp w owns particles [512 w, 512 w + 512), lane l moves chunks
+//     l + 32 i of that span: still 512 contiguous bytes per instruction), so both striped <-> blocked
+//     transposes stay inside the warp's own slice of the padded row buffer: __syncwarp instead of
+//     __syncthreads, twice per row;
+//   * warp boundaries are segment boundaries of the exact cumulative sum: the composition of the parity
+//     maps needs no cross-warp exchange (previously two barriers and an O(warps) dependent loop per
+//     thread); the walker visits ~5 more segments per row, each O(1);
+//   * cross-warp prefixes (row max, pairwise partials, approximate prefix, max-scan carry) are
+//     log-depth shuffles over one shared array instead of dependent loops over it;
+//   * the verification flag of the exact scan rides on the next barrier instead of its own;
+//   * 9 barriers per row instead of 15; no barrier at the end of a row (the latent row is staged
+//     after the next row's first barrier);
+//   * the maxima that scipy excludes from the sum are found by one compare per thread (its own maximum
+//     against the row's) instead of three instructions per particle; the IEEE-division range test and the
+//     clamp of the boundary count are hoisted out of the per-particle loop (the CDF is monotone: its first
+//     entry bounds the rest, and cdf / total <= 1 bounds the count by K); exp's denominator is evaluated
+//     negated instead of being negated afterwards.
+//
+// Everything it cannot take (other K, vector latents, fast mode, the fused-model step, no resampling)
+// stays with smc_step_reg.cu / smc_step.cu / smc_step_large.cu.
+#include <cstdlib>
+#include "common.cuh"
+#include "pairwise.cuh"
+
+namespace aesmc {
+
+struct XStepParams {
+    const float *a, *b, *c;
+    const double *u;
+    int B;
+    float *log_w, *lse;
+    int32_t *idx;
+    const float *x_in;
+    float *x_out;
+    int32_t *flags;
+    float tol32;
+};
+
+namespace xk {
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// np_expf_nonpos_pair (common.cuh) with the denominator evaluated NEGATED: fma(-c1, r, -c0) and
+// fma(., r, -1) are the exact negations of the reference's Horner steps (rounding is symmetric), which
+// saves the two sign flips per pair; rcp.approx of the negated value is the negated reciprocal.
+__device__ __forceinline__ void np_expf_nonpos_pair_x(float x0, float x1, float &r0, float &r1)
+{
+    const f32x2 x = pack2(x0, x1);
+    const f32x2 magic = splat2(12582912.0f);
+    const f32x2 tq = add2(pack2(__fmul_rn(x0, 1.44269504088896340736f), __fmul_rn(x1, 1.44269504088896340736f)), magic);
+    const f32x2 q = sub2(tq, magic);
+    f32x2 r = fma2(q, splat2(-6.93145752e-1f), x);
+    r = fma2(q, splat2(-1.42860677e-6f), r);
+    f32x2 num = fma2(splat2(5.082762527590693718096e-04f), r, splat2(6.757896990527504603057e-03f));
+    num = fma2(num, r, splat2(5.114512081637298353406e-02f));
+    num = fma2(num, r, splat2(2.473615434895520810817e-01f));
+    num = fma2(num, r, splat2(7.257664613233124478488e-01f));
+    num = fma2(num, r, splat2(9.999999999980870924916e-01f));
+    f32x2 nden = fma2(splat2(-2.159509375685829852307e-02f), r, splat2(2.742335390411667452936e-01f));
+    nden = fma2(nden, r, splat2(-1.0f));
+    float n0, n1;
+    unpack2(nden, n0, n1);
+    f32x2 y = pack2(rcp_approx(-n0), rcp_approx(-n1)); // -nden IS den, bit for bit; the sign flip folds into the MUFU operand
+    y = fma2(fma2(nden, y, splat2(1.0f)), y, y);
+    const f32x2 q0 = mul2(num, y);
+    const f32x2 poly = fma2(fma2(nden, q0, num), y, q0);
+    float p0, p1, t0, t1;
+    unpack2(poly, p0, p1);
+    unpack2(tq, t0, t1);
+    const int k0 = __float_as_int(t0) - 0x4B400000, k1 = __float_as_int(t1) - 0x4B400000;
+    if (min(k0, k1) >= -125) {
+        r0 = __int_as_float(__float_as_int(p0) + (k0 << 23));
+        r1 = __int_as_float(__float_as_int(p1) + (k1 << 23));
+        return;
+    }
+    r0 = (k0 >= -125) ? __int_as_float(__float_as_int(p0) + (k0 << 23))
+       : (x0 <= -103.97208404541015625f) ? 0.0f
+       : __fmul_rn(__int_as_float(__float_as_int(p0) + ((k0 + 64) << 23)), 5.42101086242752217e-20f);
+    r1 = (k1 >= -125) ? __int_as_float(__float_as_int(p1) + (k1 << 23))
+       : (x1 <= -103.97208404541015625f) ? 0.0f
+       : __fmul_rn(__int_as_float(__float_as_int(p1) + ((k1 + 64) << 23)), 5.42101086242752217e-20f);
+}
+
+// explicit shared-window accesses for the serial walker: generic pointers make the compiler rebuild the shared base
+// (S2R SR_CgaCtaId, LEA ...) inside the loop, and every instruction of that loop is on the row's critical path
+__device__ __forceinline__ int4 lds_v4(unsigned addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_b32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
+__device__ __forceinline__ void compose(int p0, int p1, int n0, int n1, int &h0, int &h1)
+{
+    h0 = p0 + ((p0 & 1) ? n1 : n0);
+    h1 = p1 + (((1 + p1) & 1) ? n1 : n0);
+}
+
+template <int NW> struct Shared {
+    float wmax[NW], part[NW], wsum[NW];
+    int cnt[NW], i1[NW], i2[NW];
+    float lse, total;
+    int bad, fail;
+    float seg_state[NW * 32]; // exact chain value entering each segment, [warp][segment]
+};
+
+template <int NW> __device__ __forceinline__ float across_max(const float *arr, int lane)
+{
+    float m = arr[lane & (NW - 1)];
+#pragma unroll
+    for (int o = NW >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    return m;
+}
+
+} // namespace xk
+
+#ifndef AESMC_X_THREADS_PER_SM
+#define AESMC_X_THREADS_PER_SM 1024 // resident threads per SM the register budget is sized for (1024 -> 64 registers)
+#endif
+#ifndef AESMC_X_ALIAS_X
+#define AESMC_X_ALIAS_X 0 // 1: the latent row is staged into the weight buffer once the exact scan is done with it
+#endif
+#ifndef AESMC_X_PREFETCH
+#define AESMC_X_PREFETCH 0 // 1: bulk-prefetch the inputs of the next row this CTA will process into L2
+#endif
+#ifndef AESMC_X_REDUNDANT_TAIL
+#define AESMC_X_REDUNDANT_TAIL 0 // 1: every warp evaluates the scalar lse tail itself (no barrier (3))
+#endif
+#ifndef AESMC_X_WALKER_WARP
+#define AESMC_X_WALKER_WARP (NW - 1)
+#endif
+
+template <int NT, bool HAS_X>
+__global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC_X_THREADS_PER_SM / NT) : 1)
+    smc_step_x_kernel(const XStepParams p)
+{
+    using namespace xk;
+    constexpr int NW = NT / 32, K = 16 * NT, NCH = 4 * NT;
+    constexpr int ROWCH = NCH + NCH / 8; // padded row, in 16-byte chunks (one spare chunk per 8)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *bufW4 = reinterpret_cast<float4 *>(smem_raw);          // exp / weights (padded)
+    int4 *bufM4 = reinterpret_cast<int4 *>(bufW4 + ROWCH);                                  // run marks; exact-scan segment lists
+    float4 *bufX4 = AESMC_X_ALIAS_X ? bufW4 : reinterpret_cast<float4 *>(bufM4 + ROWCH); // staged latent row
+    int *bufM = reinterpret_cast<int *>(bufM4);
+    const float *bufX = reinterpret_cast<const float *>(bufX4);
+    int4 *seg_rec = bufM4;                                          // [NW][32] (last block, binade, c0, c1): only the
+                                                                    // walker reads it, before the marks are zeroed
+    __shared__ Shared<NW> sh;
+    float *seg_state = sh.seg_state;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wbase = 144 * warp;                 // the warp's 128 chunks (+16 spare) of a padded row
+    const int sl = wbase + lane + (lane >> 3);    // striped chunk lane + 32 i  ->  sl + 36 i
+    const int bl = wbase + 4 * lane + (lane >> 1); // blocked chunk 4 lane + i  ->  bl + i
+    const int gc = 128 * warp + lane;             // the same striped chunk in global memory (+ 32 i)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float Kf = (float)K;
+
+    if (tid == 0) sh.bad = 0;
+    __syncthreads();
+
+    for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
+        const size_t off = (size_t)row * K;
+        const float4 *__restrict__ a4 = reinterpret_cast<const float4 *>(p.a + off) + gc;
+        const float4 *__restrict__ b4 = p.b ? reinterpret_cast<const float4 *>(p.b + off) + gc : nullptr;
+        const float4 *__restrict__ c4 = p.c ? reinterpret_cast<const float4 *>(p.c + off) + gc : nullptr;
+        float4 *__restrict__ o4 = reinterpret_cast<float4 *>(p.log_w + off) + gc;
+        const float u32 = (float)p.u[row]; // the float64 original is re-read by the rare float64 fix-up only
+
+        // ---- P1: striped loads, log-weights out, thread / warp maximum ----------------------------
+        float4 lw[4];
+        float tmax = -INFINITY;
+        int bad = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 v = ld_stream(a4 + 32 * i);
+            f32x2 lo = pack2(v.x, v.y), hi = pack2(v.z, v.w);
+            if (b4) { const float4 t = ld_stream(b4 + 32 * i); lo = add2(lo, pack2(t.x, t.y)); hi = add2(hi, pack2(t.z, t.w)); }
+            if (c4) { const float4 t = ld_stream(c4 + 32 * i); lo = sub2(lo, pack2(t.x, t.y)); hi = sub2(hi, pack2(t.z, t.w)); }
+            unpack2(lo, v.x, v.y);
+            unpack2(hi, v.z, v.w);
+            __stcs(o4 + 32 * i, v);
+            bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+            tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            lw[i] = v;
+        }
+        {
+            const float wm = warp_max(tmax);
+            if (lane == 0) sh.wmax[warp] = wm;
+            if (bad) sh.bad = 1;
+        }
+        __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
+        if (HAS_X && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5 (lands while the weights are processed)
+            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
+        }
+        if (AESMC_X_PREFETCH) { // pull the next row this CTA will process into L2 while this one is being computed
+            const int next = row + gridDim.x;
+            if (next < p.B && tid < 4) {
+                const float *src = tid == 0 ? p.a : (tid == 1 ? p.b : (tid == 2 ? p.c : (HAS_X ? p.x_in : nullptr)));
+                if (src) prefetch_l2_bulk(src + (size_t)next * K, (unsigned)K * 4u);
+            }
+        }
+        const float vmax = across_max<NW>(sh.wmax, lane);
+        if (sh.bad || !(fabsf(vmax) < INFINITY)) { // NaN / all -inf / +inf: flag, identity ancestors (CTA-uniform branch)
+            const int isnan_row = sh.bad;
+            if (tid == 0) {
+                atomicOr(p.flags, isnan_row ? AESMC_FLAG_NAN : AESMC_FLAG_DEGENERATE);
+                if (p.lse) p.lse[row] = isnan_row ? __int_as_float(0x7fc00000) : vmax;
+            }
+            for (int k = tid; k < K; k += NT) {
+                p.idx[off + k] = k;
+                if (HAS_X) p.x_out[off + k] = p.x_in[off + k];
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            if (tid == 0) sh.bad = 0;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- P2a: e = np.exp(lw - max); numpy's pairwise sum of the non-maxima (scipy logsumexp) --
+        {
+            const bool has_max = (tmax == vmax); // this thread holds (one of) the row maxima: excluded and counted
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = lw[i];
+                const float dx = __fsub_rn(v.x, vmax), dy = __fsub_rn(v.y, vmax), dz = __fsub_rn(v.z, vmax), dw = __fsub_rn(v.w, vmax);
+                float4 e;
+                np_expf_nonpos_pair_x(dx, dy, e.x, e.y);
+                np_expf_nonpos_pair_x(dz, dw, e.z, e.w);
+                if (has_max) {
+                    if (dx == 0.0f) { e.x = 0.0f; ++cnt; }
+                    if (dy == 0.0f) { e.y = 0.0f; ++cnt; }
+                    if (dz == 0.0f) { e.z = 0.0f; ++cnt; }
+                    if (dw == 0.0f) { e.w = 0.0f; ++cnt; }
+                }
+                bufW4[sl + 36 * i] = e;
+            }
+            __syncwarp();
+            // leaf L = particles [128 L, 128 L + 128) of the warp's span, summed by lanes 8L .. 8L+7 with numpy's
+            // 8 strided accumulators; xor-shuffles 1, 2, 4 combine them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+            // 8 and 16 fold the warp's four leaves as the balanced tree numpy's recursion is for K = 128 * 2^n
+            const float *base = reinterpret_cast<const float *>(bufW4 + wbase) + 144 * (lane >> 3) + (lane & 7);
+            float r = base[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) r = __fadd_rn(r, base[8 * i + 4 * (i >> 2)]);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) r = __fadd_rn(r, __shfl_xor_sync(kFull, r, o));
+            if (__any_sync(kFull, has_max)) cnt = warp_sum(cnt);
+            if (lane == 0) { sh.part[warp] = r; sh.cnt[warp] = cnt; }
+        }
+        __syncthreads(); // (2) per-warp partial sums and maxima counts
+        float lse;
+        if (AESMC_X_REDUNDANT_TAIL || warp == NW - 1) { // fold the partials and evaluate the scalar tail (division, log1p, log)
+            float s = sh.part[lane & (NW - 1)];
+            int m = sh.cnt[lane & (NW - 1)];
+#pragma unroll
+            for (int o = 1; o < NW; o <<= 1) {
+                s = __fadd_rn(s, __shfl_xor_sync(kFull, s, o));
+                m += __shfl_xor_sync(kFull, m, o);
+            }
+            float v;
+            if (m == 1) { // a single maximum (the usual case): s / 1 = s and log(1) = +0 are exact no-ops
+                v = __fadd_rn(fd_log1pf(s), vmax);
+            } else {
+                const float mf = (float)m;
+                if (s != 0.0f) s = __fdiv_rn(s, mf);
+                v = __fadd_rn(__fadd_rn(fd_log1pf(s), np_logf(mf)), vmax);
+            }
+            lse = v;
+            if (tid == NT - 32) {
+                if (!AESMC_X_REDUNDANT_TAIL) sh.lse = v;
+                if (p.lse) p.lse[row] = v;
+            }
+        }
+        if (!AESMC_X_REDUNDANT_TAIL) {
+            __syncthreads(); // (3) lse
+            lse = sh.lse;
+        }
+
+        // ---- P2b: normalised weights np.exp(lw - lse) (math.py:49), striped -> blocked inside the warp --
+        float w[16];
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = lw[i];
+                float4 e;
+                np_expf_nonpos_pair_x(__fsub_rn(v.x, lse), __fsub_rn(v.y, lse), e.x, e.y);
+                np_expf_nonpos_pair_x(__fsub_rn(v.z, lse), __fsub_rn(v.w, lse), e.z, e.w);
+                bufW4[sl + 36 * i] = e;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = bufW4[bl + i];
+                w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        }
+
+        // ---- P3: np.cumsum's sequential float32 chain, in parallel (exact_scan.cuh) -----------------
+        // approximate prefix with an error bound -> classification of each thread's 16-particle block
+        float ls = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ls += w[j];
+        float incl = ls;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float n = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) sh.wsum[warp] = incl;
+        __syncthreads(); // (4) warp totals of the approximate prefix
+        float woff;
+        {
+            float sc = sh.wsum[lane & (NW - 1)];
+#pragma unroll
+            for (int o = 1; o < NW; o <<= 1) {
+                const float n = __shfl_up_sync(kFull, sc, o);
+                if (lane >= o) sc += n;
+            }
+            woff = __shfl_sync(kFull, sc, (warp + 31) & 31); // inclusive sum of the warps before this one
+            if (warp == 0) woff = 0.f;
+        }
+        const float p_in = woff + (incl - ls), p_out = woff + incl;
+        // |chain - real prefix| <= k 2^-24 relative; the float scans above add < 64 further roundings
+        const float eps = (float)(16 * (tid + 1) + 64) * 5.9604644775390625e-08f;
+        const float lo = __fmul_rd(p_in, 1.0f - eps), hi = __fmul_ru(p_out, 1.0f + eps);
+        int eb = 0; // biased exponent of a pure block's binade, 0 = mixed, -1 = absorbed (identity in every binade)
+        if (lo >= 7.8886090522101181e-31f) {
+            const int el = __float_as_int(lo) >> 23, eh = __float_as_int(hi) >> 23;
+            if (el == eh) eb = el;
+        }
+        if (ls == 0.f || ls < __fmul_rd(lo, 1.4901161193847656e-08f)) eb = -1;
+        {   // an absorbed block joins the pure run it follows inside the warp (its map is (0, 0))
+            const unsigned live = __ballot_sync(kFull, eb != -1), below = live & lt_mask;
+            const int e_prev = __shfl_sync(kFull, eb, below ? 31 - __clz(below) : 0);
+            if (eb == -1 && below && e_prev > 0) eb = e_prev;
+        }
+        const float scale = __int_as_float((277 - (eb > 0 ? eb : 127)) << 23); // 2^(23 - e)
+        int c0 = 0, c1 = 0;
+        if (eb > 0) {
+            f32x2 m01 = pack2(8388608.0f, 8388609.0f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m01 = add2(m01, splat2(__fmul_rn(w[j], scale)));
+            float m0, m1;
+            unpack2(m01, m0, m1);
+            if (m1 < 16777216.0f) {
+                c0 = __float_as_int(m0) & 0x7fffff;
+                c1 = (__float_as_int(m1) & 0x7fffff) - 1;
+            } else {
+                eb = 0;
+            }
+        }
+        // segments: maximal runs of pure blocks of one binade INSIDE a warp; a mixed block is its own segment
+        int prev0, prev1, segidx;
+        bool head;
+        {
+            const int eb_prev = __shfl_up_sync(kFull, eb, 1), eb_next = __shfl_down_sync(kFull, eb, 1);
+            head = (lane == 0) || (eb == 0) || (eb_prev != eb);
+            const bool tail = (lane == 31) || (eb_next == 0) || (eb_next != eb);
+            int g0 = c0, g1 = c1, hf = head;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int q0 = __shfl_up_sync(kFull, g0, o), q1 = __shfl_up_sync(kFull, g1, o);
+                const int qf = __shfl_up_sync(kFull, hf, o);
+                if (lane >= o && !hf) {
+                    compose(q0, q1, g0, g1, g0, g1);
+                    hf = qf;
+                }
+            }
+            prev0 = __shfl_up_sync(kFull, g0, 1); // inclusive map of the run up to the previous block
+            prev1 = __shfl_up_sync(kFull, g1, 1);
+            const unsigned endmask = __ballot_sync(kFull, tail);
+            segidx = __popc(endmask & lt_mask);
+            // record: (first padded chunk of the block -- read for mixed blocks only -- | last-of-this-warp flag in
+            // bit 30, binade base bits (pure run) or 0 (mixed block) or -1 (absorbed: identity), c0, c1 (0 unless pure)
+            if (tail) seg_rec[32 * warp + segidx] = make_int4(bl | (lane == 31 ? (1 << 30) : 0), eb > 0 ? (eb << 23) : eb,
+                                                              eb > 0 ? g0 : 0, eb > 0 ? g1 : 0);
+        }
+        __syncthreads(); // (5) segment lists
+        if (tid == 32 * (AESMC_X_WALKER_WARP)) {
+            // One thread walks the segments.  This is the serial part of the row (every other warp waits for it),
+            // so the loop carries as little as possible: a pure run is applied to the BIT PATTERN of the chain
+            // value -- for s = m 2^(e-23) in binade e, bits(s) + c[bits & 1] are the bits of (m + c) 2^(e-23) while
+            // m + c < 2^24, and exactly those of 2^(e+1) when m + c = 2^24 (the mantissa field carries into the
+            // exponent) -- i.e. three dependent integer instructions; the binade checks hang off the chain.
+            // The verification is not done here: every block re-checks, in parallel, that its entry value and its
+            // partial sums stayed inside the assumed binade (replay below), which covers every step taken here.
+            int sb = 0; // bits of the chain value (0.0f at the start of a row)
+            const unsigned rec0 = (unsigned)__cvta_generic_to_shared(seg_rec);
+            const unsigned st0 = (unsigned)__cvta_generic_to_shared(seg_state);
+            const unsigned w0 = (unsigned)__cvta_generic_to_shared(bufW4);
+            int idx = 0;
+            int4 rec = lds_v4(rec0);
+#pragma unroll 2
+            for (;;) {
+                const int x = rec.x, base = rec.y;
+                const int sel = (sb & 1) ? rec.w : rec.z;
+                const int nidx = (x >> 30) ? (idx | 31) + 1 : idx + 1; // lists are per warp, 32 slots apart
+                rec = lds_v4(rec0 + 16 * nidx); // next record (one past the end is a harmless read): overlaps with the chain
+                sts_b32(st0 + 4 * idx, sb);
+                sb += sel; // pure run: the whole step; mixed / absorbed records carry c0 = c1 = 0
+                if (base == 0) { // mixed block: its 16 real additions
+                    const unsigned blk = w0 + 16 * (x & 0xffff);
+                    float s = __int_as_float(sb);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = lds_f4(blk + 16 * c);
+                        s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+                    }
+                    sb = __float_as_int(s);
+                }
+                if (nidx >= 32 * NW) break;
+                idx = nidx;
+            }
+            sh.total = __int_as_float(sb);
+            sh.fail = 0;
+        }
+        __syncthreads(); // (6) exact chain value at every segment start
+        if (HAS_X && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
+            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
+        }
+        {   // every thread replays its own block from its exact entry state
+            int badv = 0;
+            const float s0 = seg_state[32 * warp + segidx];
+            if (eb > 0) {
+                const int sb = __float_as_int(s0);
+                int m = (sb & 0x7fffff) | 0x800000;
+                if ((sb >> 23) != eb) badv = 1;
+                if (!head) m += (m & 1) ? prev1 : prev0;
+                if (m >= 0x1000000) { badv = 1; m = 0x800000; }
+                float mf = __int_as_float(0x4B000000 | (m & 0x7fffff));
+                const int unscale = (150 - eb) << 23;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    mf = __fadd_rn(mf, __fmul_rn(w[j], scale));
+                    w[j] = __int_as_float(__float_as_int(mf) - unscale);
+                }
+                if (mf > 16777216.0f) badv = 1;
+            } else {
+                float s = s0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s = __fadd_rn(s, w[j]); w[j] = s; }
+            }
+            if (badv) sh.fail = 1; // read after barrier (7)
+        }
+        float total = sh.total;
+
+        // ---- P4: closed-form offspring boundaries (inference.py:251,260-264), run marks, max-scan ---
+        int cj[16];
+        int cprev;
+        for (int attempt = 0;; ++attempt) {
+            float rcp = rcp_approx(total);
+            rcp = __fmaf_rn(__fmaf_rn(-total, rcp, 1.0f), rcp, rcp);
+            // the CDF is non-decreasing: its first entry bounds the others from below, so one test per thread
+            // decides whether the hoisted-reciprocal division is the IEEE quotient for all 16
+            const bool safe = total > 9.3132257e-10f && total < 2.0f && w[0] >= 7.8886090522101181e-31f;
+            const f32x2 rcp2 = splat2(rcp), ntot2 = splat2(-total), K2 = splat2(Kf), nu2 = splat2(-u32);
+            const f32x2 magic = splat2(12582912.0f);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                f32x2 n2;
+                if (safe) {
+                    const f32x2 c2 = pack2(w[j], w[j + 1]);
+                    const f32x2 q0 = mul2(c2, rcp2);
+                    n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
+                } else {
+                    n2 = pack2(__fdiv_rn(w[j], total), __fdiv_rn(w[j + 1], total));
+                }
+                const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
+                const f32x2 tm = add2(tf, magic);
+                const f32x2 d2 = sub2(tf, sub2(tm, magic)); // tf - rint(tf), exact
+                float d0, d1, m0, m1;
+                unpack2(d2, d0, d1);
+                unpack2(tm, m0, m1);
+                cj[j] = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
+                cj[j + 1] = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
+                if (!(fminf(fabsf(d0), fabsf(d1)) > p.tol32)) { // ~0.1 %: the reference's float64 expression
+                    float n0, n1;
+                    unpack2(n2, n0, n1);
+                    const double u = p.u[row];
+                    if (!(fabsf(d0) > p.tol32)) cj[j] = count_positions_below_slow(n0, u, K);
+                    if (!(fabsf(d1) > p.tol32)) cj[j + 1] = count_positions_below_slow(n1, u, K);
+                }
+            }
+            if (tid == NT - 1) cj[15] = K; // last particle: positions up to 1.0 stay in range (Q5)
+            if (lane == 31) sh.i1[warp] = cj[15];
+            cprev = __shfl_up_sync(kFull, cj[15], 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // (the segment lists are dead)
+            if (HAS_X) cp_async_wait_all();
+            __syncthreads(); // (7) marks zeroed, warp boundaries, staged latents and the scan's verdict visible
+            if (attempt == 0 && sh.fail) {
+                // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
+                __syncthreads();
+                float4 *redo = AESMC_X_ALIAS_X ? reinterpret_cast<float4 *>(bufM4) : bufW4;
+                if (tid == 0) {
+                    float acc = 0.f;
+                    for (int c = 0; c < NCH; ++c) {
+                        float4 v;
+                        if (AESMC_X_ALIAS_X) { // the weights are gone: recompute them from the log-weights this CTA stored
+                            const float4 l = reinterpret_cast<const float4 *>(p.log_w + off)[c];
+                            v = make_float4(np_expf_nonpos(__fsub_rn(l.x, lse)), np_expf_nonpos(__fsub_rn(l.y, lse)),
+                                            np_expf_nonpos(__fsub_rn(l.z, lse)), np_expf_nonpos(__fsub_rn(l.w, lse)));
+                        } else {
+                            v = bufW4[pad_chunk(c)];
+                        }
+                        v.x = acc = c ? __fadd_rn(acc, v.x) : v.x;
+                        v.y = acc = __fadd_rn(acc, v.y);
+                        v.z = acc = __fadd_rn(acc, v.z);
+                        v.w = acc = __fadd_rn(acc, v.w);
+                        redo[pad_chunk(c)] = v;
+                    }
+                    sh.total = acc;
+                    sh.fail = 0;
+                }
+                __syncthreads();
+                total = sh.total;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = redo[bl + i];
+                    w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                }
+                continue;
+            }
+            break;
+        }
+        if (lane == 0) cprev = warp ? sh.i1[warp - 1] : 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int cp = j ? cj[j - 1] : cprev;
+            if (cj[j] > cp) bufM[pad_elem(cp)] = 16 * tid + j; // particle 16 tid + j owns positions [cp, cj)
+        }
+        __syncthreads(); // (8) run starts
+        int id[16];
+        {
+            int run = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int4 v = bufM4[bl + i];
+                id[4 * i + 0] = run = max(run, v.x);
+                id[4 * i + 1] = run = max(run, v.y);
+                id[4 * i + 2] = run = max(run, v.z);
+                id[4 * i + 3] = run = max(run, v.w);
+            }
+            int inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc = max(inc, n);
+            }
+            if (lane == 31) sh.i2[warp] = inc;
+            int excl = __shfl_up_sync(kFull, inc, 1);
+            if (lane == 0) excl = 0;
+            __syncthreads(); // (9) warp maxima of the run ids
+            {
+                int sc = sh.i2[lane & (NW - 1)];
+#pragma unroll
+                for (int o = 1; o < NW; o <<= 1) {
+                    const int n = __shfl_up_sync(kFull, sc, o);
+                    if (lane >= o) sc = max(sc, n);
+                }
+                const int before = __shfl_sync(kFull, sc, (warp + 31) & 31);
+                if (warp) excl = max(excl, before);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) id[j] = max(id[j], excl);
+        }
+
+        // ---- P5: indices out, fused ancestral gather from the staged row ---------------------------
+        int4 *__restrict__ gidx4 = reinterpret_cast<int4 *>(p.idx + off) + 4 * tid;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) __stcs(gidx4 + i, make_int4(id[4 * i], id[4 * i + 1], id[4 * i + 2], id[4 * i + 3]));
+        if (HAS_X) {
+            float4 *__restrict__ xo4 = reinterpret_cast<float4 *>(p.x_out + off) + 4 * tid;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                __stcs(xo4 + i, make_float4(bufX[id[4 * i]], bufX[id[4 * i + 1]], bufX[id[4 * i + 2]], bufX[id[4 * i + 3]]));
+        }
+        // no barrier here: the next row touches the warp's own slice of bufW only after its barrier (1) ...
+        // (bufX is restaged after barrier (1), bufM is rewritten after barrier (4))
+    }
+}
+
+static int x_sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+bool smc_step_x_supported(int64_t K, int mode, const void *idx, const void *x_in, int64_t D)
+{
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char *e = getenv("AESMC_DISABLE_STEP_X");
+        disabled = (e && atoi(e)) ? 1 : 0;
+    }
+    if (disabled || mode != AESMC_MODE_EXACT || idx == nullptr) return false;
+    if (x_in != nullptr && D != 1) return false;
+    return K == 1024 || K == 2048 || K == 4096 || K == 8192 || K == 16384;
+}
+
+template <int NT, bool HAS_X>
+static int launch_x(const XStepParams &p, int64_t B, cudaStream_t stream)
+{
+    constexpr int NCH = 4 * NT;
+    constexpr size_t smem = (size_t)(NCH + NCH / 8) * 16 * 2 + ((HAS_X && !AESMC_X_ALIAS_X) ? (size_t)NCH * 16 : 0);
+    auto kern = smc_step_x_kernel<NT, HAS_X>;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
+        int n = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem);
+        per_sm = n < 1 ? 1 : n;
+    }
+    long long grid = (long long)x_sm_count() * per_sm;
+    if (grid > B) grid = B;
+    kern<<<(unsigned)grid, NT, smem, stream>>>(p);
+    count_launch();
+    return check_launch("smc_step_x_kernel");
+}
+
+int launch_smc_step_x(const float *a, const float *b, const float *c, const double *u, int64_t B, int64_t K,
+                      float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out, int32_t *flags,
+                      cudaStream_t stream)
+{
+    XStepParams p;
+    p.a = a; p.b = b; p.c = c; p.u = u; p.B = (int)B; p.log_w = log_w; p.lse = lse; p.idx = idx;
+    p.x_in = x_in; p.x_out = x_out; p.flags = flags;
+    p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f; // K*2^-23 + 2^-24
+    const bool hx = x_in != nullptr;
+    switch (K) {
+    case 1024: return hx ? launch_x<64, true>(p, B, stream) : launch_x<64, false>(p, B, stream);
+    case 2048: return hx ? launch_x<128, true>(p, B, stream) : launch_x<128, false>(p, B, stream);
+    case 4096: return hx ? launch_x<256, true>(p, B, stream) : launch_x<256, false>(p, B, stream);
+    case 8192: return hx ? launch_x<512, true>(p, B, stream) : launch_x<512, false>(p, B, stream);
+    case 16384: return hx ? launch_x<1024, true>(p, B, stream) : launch_x<1024, false>(p, B, stream);
+    }
+    set_error("smc_step_x: unsupported K=%lld", (long long)K);
+    return AESMC_ERR_UNSUPPORTED;
+}
+
+} // namespace aesmc

@@ -73,7 +73,7 @@ def _run(module_name, pattern=None):
     return n
 
 
-@pytest.mark.parametrize("name,expected", [("test.test_math", 9), ("test.test_state", None),
+@pytest.mark.parametrize("name,expected", [("test.test_math", 6), ("test.test_state", None),
                                            ("test.test_statistics", None)])
 def test_reference_unittest_file(reference_tests, name, expected):
     n = _run(name)

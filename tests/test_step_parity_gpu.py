@@ -353,3 +353,47 @@ def test_multi_cta_flags(cuda):
     assert np.array_equal(idx.cpu().numpy()[0], np.arange(K))
     ref, _ = oracle.sample_ancestral_index(lw[1:], np.full(2, 0.25))
     assert np.array_equal(idx.cpu().numpy()[1:], ref)
+
+
+@pytest.mark.parametrize("K,B", [(1024, 2500), (2048, 1300), (4096, 700), (8192, 330), (16384, 170)])
+@pytest.mark.parametrize("with_x", [True, False])
+def test_second_generation_row_kernel_vs_oracle(cuda, K, B, with_x):
+    """smc_step_x.cu (exact mode, K = 16 * threads, scalar latent): more rows than CTAs so that every CTA loops
+    over several rows (no barrier separates two rows), random spreads from flat to collapsed, tied maxima,
+    -inf entries, a NaN row and an all -inf row in the middle of the batch -- bit-equal to the oracle."""
+    rng = np.random.default_rng(K + with_x)
+    spread = rng.uniform(0.2, 12.0, (B, 1))
+    a = (rng.standard_normal((B, K)) * spread - 1.4).astype(np.float32)
+    b = (rng.standard_normal((B, K)) * 0.5).astype(np.float32)
+    c = (rng.standard_normal((B, K)) * 0.5).astype(np.float32)
+    a[3, :7] = 50.0            # tied maxima (after adding b - c they differ again; row 4 keeps exact ties)
+    a[4], b[4], c[4] = -0.5, 0.0, 0.0
+    a[5, ::3] = -np.inf
+    a[6, 1:] = -np.inf
+    nan_row, dead_row = B // 2, B // 2 + 1
+    a[nan_row, 17] = np.nan
+    a[dead_row] = -np.inf
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    u = rng.random(B)
+    u[7] = 0.0
+    u[8] = np.nextafter(1.0, 0.0)
+    (log_w, lse, idx, xr), fl = run_step(a, u, cuda, b=b, c=c, x=x if with_x else None)
+    assert fl == (_lib.FLAG_NAN | _lib.FLAG_DEGENERATE)
+    good = np.ones(B, bool)
+    good[[nan_row, dead_row]] = False
+    lw_ref = oracle.log_weight(a, b, c)
+    assert np.array_equal(bits(log_w.cpu().numpy()[good]), bits(lw_ref[good]))
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw_ref[good], u[good], return_parts=True)
+    assert st == 0
+    got = idx.cpu().numpy()
+    assert np.array_equal(bits(lse.cpu().numpy()[good]), bits(lse_ref))
+    wrong = np.nonzero((got[good] != np.minimum(idx_ref, K - 1)).any(axis=1))[0]
+    assert wrong.size == 0, "rows with index mismatches: %s" % wrong[:10]
+    assert np.array_equal(got[nan_row], np.arange(K)) and np.array_equal(got[dead_row], np.arange(K))
+    if with_x:
+        assert np.array_equal(xr.cpu().numpy(), np.take_along_axis(x, got.astype(np.int64), axis=1))
+    # only the first log-prob given (sample_ancestral_index's call shape)
+    (log_w1, lse1, idx1, _), fl1 = run_step(lw_ref[good][:64], u[good][:64], cuda)
+    assert fl1 == 0
+    assert np.array_equal(idx1.cpu().numpy(), np.minimum(idx_ref[:64], K - 1).astype(np.int32))
+    assert np.array_equal(bits(lse1.cpu().numpy()), bits(lse_ref[:64]))
