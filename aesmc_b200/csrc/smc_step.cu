@@ -304,8 +304,9 @@ int launch_smc_step_large(const float *, const float *, const float *, const dou
                           int32_t *, const float *, float *, int64_t, int32_t *, int, void *, int64_t, cudaStream_t);
 bool smc_step_reg_supported(int64_t K, bool vec);
 bool smc_step_x_supported(int64_t K, int mode, const void *idx, const void *x_in, int64_t D);
-int launch_smc_step_x(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
-                      int32_t *, const float *, float *, int32_t *, cudaStream_t);
+int launch_smc_step_x(const float *a, const float *b, const float *c, const double *u, int64_t B, int64_t K,
+                      float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out, int32_t *flags,
+                      cudaStream_t stream);
 int launch_smc_step_reg(const float *, const float *, const float *, const double *, int64_t, int64_t, float *, float *,
                         int32_t *, const float *, float *, int64_t, int32_t *, int, cudaStream_t);
 

@@ -33,20 +33,11 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "pairwise.cuh"
+#include "lg_model.cuh"
+#include "step_x.cuh"
 
 namespace aesmc {
 
-struct XStepParams {
-    const float *a, *b, *c;
-    const double *u;
-    int B;
-    float *log_w, *lse;
-    int32_t *idx;
-    const float *x_in;
-    float *x_out;
-    int32_t *flags;
-    float tol32;
-};
 
 namespace xk {
 
@@ -146,27 +137,31 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 
 } // namespace xk
 
-#ifndef AESMC_X_THREADS_PER_SM
-#define AESMC_X_THREADS_PER_SM 1024 // resident threads per SM the register budget is sized for (1024 -> 64 registers)
-#endif
-#ifndef AESMC_X_ALIAS_X
-#define AESMC_X_ALIAS_X 0 // 1: the latent row is staged into the weight buffer once the exact scan is done with it
-#endif
 #ifndef AESMC_X_PREFETCH
-#define AESMC_X_PREFETCH 0 // 1: bulk-prefetch the inputs of the next row this CTA will process into L2
+#define AESMC_X_PREFETCH 0 // 1: bulk-prefetch the inputs of the next row this CTA will process into L2 (measured: no gain)
 #endif
 #ifndef AESMC_X_REDUNDANT_TAIL
-#define AESMC_X_REDUNDANT_TAIL 0 // 1: every warp evaluates the scalar lse tail itself (no barrier (3))
+#define AESMC_X_REDUNDANT_TAIL 0 // 1: every warp evaluates the scalar lse tail itself, no barrier (3) (measured: -1 %)
 #endif
 #ifndef AESMC_X_WALKER_WARP
 #define AESMC_X_WALKER_WARP (NW - 1)
 #endif
 
-template <int NT, bool HAS_X>
-__global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC_X_THREADS_PER_SM / NT) : 1)
+// ALIAS (plain step with a latent row to gather): the latent row is staged into the weight buffer once the exact
+// scan is done with it -- 36 KB of shared memory per 256-thread CTA instead of 52, so five CTAs fit an SM, and the
+// register budget is sized for them (48 registers; measured 151 us against 156 us for four CTAs at 64 registers).
+// The fused-model step produces the latents itself in P1 and keeps the separate staging row (four CTAs per SM).
+template <bool HAS_X, bool FUSED> struct XConfig {
+    static constexpr bool kAlias = HAS_X && !FUSED;
+    static constexpr int kThreadsPerSM = FUSED ? 1024 : 1280;
+};
+
+template <int NT, bool HAS_X, bool FUSED>
+__global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT) > 0 ? (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT) : 1)
     smc_step_x_kernel(const XStepParams p)
 {
     using namespace xk;
+    constexpr bool AESMC_X_ALIAS_X = XConfig<HAS_X, FUSED>::kAlias;
     constexpr int NW = NT / 32, K = 16 * NT, NCH = 4 * NT;
     constexpr int ROWCH = NCH + NCH / 8; // padded row, in 16-byte chunks (one spare chunk per 8)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -193,28 +188,67 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
 
     for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
         const size_t off = (size_t)row * K;
-        const float4 *__restrict__ a4 = reinterpret_cast<const float4 *>(p.a + off) + gc;
-        const float4 *__restrict__ b4 = p.b ? reinterpret_cast<const float4 *>(p.b + off) + gc : nullptr;
-        const float4 *__restrict__ c4 = p.c ? reinterpret_cast<const float4 *>(p.c + off) + gc : nullptr;
-        float4 *__restrict__ o4 = reinterpret_cast<float4 *>(p.log_w + off) + gc;
         const float u32 = (float)p.u[row]; // the float64 original is re-read by the rare float64 fix-up only
 
-        // ---- P1: striped loads, log-weights out, thread / warp maximum ----------------------------
         float4 lw[4];
         float tmax = -INFINITY;
         int bad = 0;
+        if (FUSED) {
+            // propose x ~ q(. | x_prev, y), then log_w = (log p(x | x_prev) + log p(y | x)) - log q(x | x_prev, y), each
+            // term with torch.distributions.Normal's float32 arithmetic (lg_model.cuh)
+            const float yv = p.y[row];
+            const float qoff = p.q_off ? p.q_off[row] : p.q.off;
+            const unsigned long long seed = p.seed_dev ? *p.seed_dev : p.seed;
+            const float rcp_t = refined_rcp(p.t.two_var), rcp_e = refined_rcp(p.e.two_var), rcp_q = refined_rcp(p.q.two_var);
+            const float4 *__restrict__ xp4 = p.x_prev ? reinterpret_cast<const float4 *>(p.x_prev + off) + gc : nullptr;
+            const float4 *__restrict__ nz4 = p.noise ? reinterpret_cast<const float4 *>(p.noise + off) + gc : nullptr;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 v = ld_stream(a4 + 32 * i);
-            f32x2 lo = pack2(v.x, v.y), hi = pack2(v.z, v.w);
-            if (b4) { const float4 t = ld_stream(b4 + 32 * i); lo = add2(lo, pack2(t.x, t.y)); hi = add2(hi, pack2(t.z, t.w)); }
-            if (c4) { const float4 t = ld_stream(c4 + 32 * i); lo = sub2(lo, pack2(t.x, t.y)); hi = sub2(hi, pack2(t.z, t.w)); }
-            unpack2(lo, v.x, v.y);
-            unpack2(hi, v.z, v.w);
-            __stcs(o4 + 32 * i, v);
-            bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-            tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-            lw[i] = v;
+            for (int i = 0; i < 4; ++i) {
+                const float4 xp = xp4 ? ld_stream(xp4 + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 ep = nz4 ? ld_stream(nz4 + 32 * i)
+                                      : philox_normal4(seed, p.stream_offset, (unsigned long long)off / 4 + gc + 32 * i);
+                const f32x2 xs2[2] = {pack2(xp.x, xp.y), pack2(xp.z, xp.w)}, es2[2] = {pack2(ep.x, ep.y), pack2(ep.z, ep.w)};
+                float xo[4], lo[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f32x2 loc_q = add2(mul2_sep(xs2[h], p.q.mult), splat2(qoff));
+                    const f32x2 x2 = add2(loc_q, mul2_sep(es2[h], p.q.scale)); // Normal.rsample
+                    const f32x2 lq = normal_log_prob2(x2, loc_q, p.q.two_var, rcp_q, p.q.log_scale, p.half_log_2pi);
+                    const f32x2 lt = p.q_same_t ? lq
+                                   : normal_log_prob2(x2, add2(mul2_sep(xs2[h], p.t.mult), splat2(p.t.off)),
+                                                      p.t.two_var, rcp_t, p.t.log_scale, p.half_log_2pi);
+                    const f32x2 le = normal_log_prob2(splat2(yv), add2(mul2_sep(x2, p.e.mult), splat2(p.e.off)),
+                                                      p.e.two_var, rcp_e, p.e.log_scale, p.half_log_2pi);
+                    unpack2(x2, xo[2 * h], xo[2 * h + 1]);
+                    unpack2(sub2(add2(lt, le), lq), lo[2 * h], lo[2 * h + 1]);
+                }
+                const float4 xv = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                const float4 v = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                if (p.x_new) __stcs(reinterpret_cast<float4 *>(p.x_new + off) + gc + 32 * i, xv);
+                if (p.log_w) __stcs(reinterpret_cast<float4 *>(p.log_w + off) + gc + 32 * i, v);
+                bufX4[gc + 32 * i] = xv; // the gather source of P5 (the previous row's readers passed the barrier below)
+                bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                lw[i] = v;
+            }
+        } else {
+            const float4 *__restrict__ a4 = reinterpret_cast<const float4 *>(p.a + off) + gc;
+            const float4 *__restrict__ b4 = p.b ? reinterpret_cast<const float4 *>(p.b + off) + gc : nullptr;
+            const float4 *__restrict__ c4 = p.c ? reinterpret_cast<const float4 *>(p.c + off) + gc : nullptr;
+            float4 *__restrict__ o4 = reinterpret_cast<float4 *>(p.log_w + off) + gc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 v = ld_stream(a4 + 32 * i);
+                f32x2 lo = pack2(v.x, v.y), hi = pack2(v.z, v.w);
+                if (b4) { const float4 t = ld_stream(b4 + 32 * i); lo = add2(lo, pack2(t.x, t.y)); hi = add2(hi, pack2(t.z, t.w)); }
+                if (c4) { const float4 t = ld_stream(c4 + 32 * i); lo = sub2(lo, pack2(t.x, t.y)); hi = sub2(hi, pack2(t.z, t.w)); }
+                unpack2(lo, v.x, v.y);
+                unpack2(hi, v.z, v.w);
+                __stcs(o4 + 32 * i, v);
+                bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                lw[i] = v;
+            }
         }
         {
             const float wm = warp_max(tmax);
@@ -222,7 +256,7 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
             if (bad) sh.bad = 1;
         }
         __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
-        if (HAS_X && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5 (lands while the weights are processed)
+        if (HAS_X && !FUSED && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
@@ -242,10 +276,10 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
                 if (p.lse) p.lse[row] = isnan_row ? __int_as_float(0x7fc00000) : vmax;
             }
             for (int k = tid; k < K; k += NT) {
-                p.idx[off + k] = k;
-                if (HAS_X) p.x_out[off + k] = p.x_in[off + k];
+                if (p.idx) p.idx[off + k] = k;
+                if (HAS_X) p.x_out[off + k] = FUSED ? bufX[k] : p.x_in[off + k];
             }
-            cp_async_wait_all();
+            if (!FUSED) cp_async_wait_all();
             __syncthreads();
             if (tid == 0) sh.bad = 0;
             __syncthreads();
@@ -452,7 +486,7 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
             sh.fail = 0;
         }
         __syncthreads(); // (6) exact chain value at every segment start
-        if (HAS_X && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
+        if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
@@ -525,7 +559,7 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
             cprev = __shfl_up_sync(kFull, cj[15], 1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // (the segment lists are dead)
-            if (HAS_X) cp_async_wait_all();
+            if (HAS_X && !FUSED) cp_async_wait_all();
             __syncthreads(); // (7) marks zeroed, warp boundaries, staged latents and the scan's verdict visible
             if (attempt == 0 && sh.fail) {
                 // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
@@ -605,9 +639,11 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
         }
 
         // ---- P5: indices out, fused ancestral gather from the staged row ---------------------------
-        int4 *__restrict__ gidx4 = reinterpret_cast<int4 *>(p.idx + off) + 4 * tid;
+        if (!FUSED || p.idx != nullptr) { // (the fused-model step may resample without storing the ancestors)
+            int4 *__restrict__ gidx4 = reinterpret_cast<int4 *>(p.idx + off) + 4 * tid;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) __stcs(gidx4 + i, make_int4(id[4 * i], id[4 * i + 1], id[4 * i + 2], id[4 * i + 3]));
+            for (int i = 0; i < 4; ++i) __stcs(gidx4 + i, make_int4(id[4 * i], id[4 * i + 1], id[4 * i + 2], id[4 * i + 3]));
+        }
         if (HAS_X) {
             float4 *__restrict__ xo4 = reinterpret_cast<float4 *>(p.x_out + off) + 4 * tid;
 #pragma unroll
@@ -615,7 +651,9 @@ __global__ void __launch_bounds__(NT, (AESMC_X_THREADS_PER_SM / NT) > 0 ? (AESMC
                 __stcs(xo4 + i, make_float4(bufX[id[4 * i]], bufX[id[4 * i + 1]], bufX[id[4 * i + 2]], bufX[id[4 * i + 3]]));
         }
         // no barrier here: the next row touches the warp's own slice of bufW only after its barrier (1) ...
-        // (bufX is restaged after barrier (1), bufM is rewritten after barrier (4))
+        // (bufX is restaged after barrier (1), bufM is rewritten after barrier (4)); the fused-model step writes the
+        // staging row in its P1, hence:
+        if (FUSED) __syncthreads();
     }
 }
 
@@ -643,12 +681,13 @@ bool smc_step_x_supported(int64_t K, int mode, const void *idx, const void *x_in
     return K == 1024 || K == 2048 || K == 4096 || K == 8192 || K == 16384;
 }
 
-template <int NT, bool HAS_X>
+template <int NT, bool HAS_X, bool FUSED>
 static int launch_x(const XStepParams &p, int64_t B, cudaStream_t stream)
 {
     constexpr int NCH = 4 * NT;
-    constexpr size_t smem = (size_t)(NCH + NCH / 8) * 16 * 2 + ((HAS_X && !AESMC_X_ALIAS_X) ? (size_t)NCH * 16 : 0);
-    auto kern = smc_step_x_kernel<NT, HAS_X>;
+    constexpr size_t smem = (size_t)(NCH + NCH / 8) * 16 * 2 +
+                            ((HAS_X && !XConfig<HAS_X, FUSED>::kAlias) ? (size_t)NCH * 16 : 0);
+    auto kern = smc_step_x_kernel<NT, HAS_X, FUSED>;
     static int per_sm = 0;
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -665,24 +704,43 @@ static int launch_x(const XStepParams &p, int64_t B, cudaStream_t stream)
     return check_launch("smc_step_x_kernel");
 }
 
+template <bool HAS_X, bool FUSED>
+static int dispatch_x(const XStepParams &p, int64_t B, int64_t K, cudaStream_t stream)
+{
+    switch (K) {
+    case 1024: return launch_x<64, HAS_X, FUSED>(p, B, stream);
+    case 2048: return launch_x<128, HAS_X, FUSED>(p, B, stream);
+    case 4096: return launch_x<256, HAS_X, FUSED>(p, B, stream);
+    case 8192: return launch_x<512, HAS_X, FUSED>(p, B, stream);
+    case 16384: return launch_x<1024, HAS_X, FUSED>(p, B, stream);
+    }
+    set_error("smc_step_x: unsupported K=%lld", (long long)K);
+    return AESMC_ERR_UNSUPPORTED;
+}
+
 int launch_smc_step_x(const float *a, const float *b, const float *c, const double *u, int64_t B, int64_t K,
                       float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out, int32_t *flags,
                       cudaStream_t stream)
 {
-    XStepParams p;
+    XStepParams p = {};
     p.a = a; p.b = b; p.c = c; p.u = u; p.B = (int)B; p.log_w = log_w; p.lse = lse; p.idx = idx;
     p.x_in = x_in; p.x_out = x_out; p.flags = flags;
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f; // K*2^-23 + 2^-24
-    const bool hx = x_in != nullptr;
-    switch (K) {
-    case 1024: return hx ? launch_x<64, true>(p, B, stream) : launch_x<64, false>(p, B, stream);
-    case 2048: return hx ? launch_x<128, true>(p, B, stream) : launch_x<128, false>(p, B, stream);
-    case 4096: return hx ? launch_x<256, true>(p, B, stream) : launch_x<256, false>(p, B, stream);
-    case 8192: return hx ? launch_x<512, true>(p, B, stream) : launch_x<512, false>(p, B, stream);
-    case 16384: return hx ? launch_x<1024, true>(p, B, stream) : launch_x<1024, false>(p, B, stream);
-    }
-    set_error("smc_step_x: unsupported K=%lld", (long long)K);
-    return AESMC_ERR_UNSUPPORTED;
+    return x_in != nullptr ? dispatch_x<true, false>(p, B, K, stream) : dispatch_x<false, false>(p, B, K, stream);
+}
+
+// the fused scalar linear-Gaussian step (aesmc_smc_step_lg_f32) in exact mode with resampling: x_out required
+bool smc_step_x_lg_supported(int64_t K, int mode, const void *x_out, const void *u)
+{
+    return smc_step_x_supported(K, mode, u /* resampling requested */, nullptr, 1) && x_out != nullptr;
+}
+
+int launch_smc_step_x_lg(const XStepParams &proto, int64_t B, int64_t K, cudaStream_t stream)
+{
+    XStepParams p = proto;
+    p.B = (int)B;
+    p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
+    return dispatch_x<true, true>(p, B, K, stream);
 }
 
 } // namespace aesmc
