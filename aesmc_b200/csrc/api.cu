@@ -34,9 +34,11 @@ int launch_smc_step(const float *, const float *, const float *, const double *,
                     int32_t *, const float *, float *, int64_t, int32_t *, int, int, void *, int64_t, cudaStream_t);
 int64_t step_workspace_bytes(int64_t B, int64_t K);
 bool smc_step_lg_supported(int64_t K);
-int launch_smc_step_lg(const float *, const float *, const float *, const float *, const float *, float,
+int launch_smc_step_lg(const float *, const float *, const float *, const float *, const float *, const float *, float,
                        unsigned long long, const unsigned long long *, unsigned long long, int64_t, int64_t,
                        const double *, float *, float *, float *, int32_t *, float *, int32_t *, int, cudaStream_t);
+int launch_lg_step_bwd(const float *, const float *, const float *, const float *, const float *, const float *, const float *,
+                       const float *, const int32_t *, int64_t, int64_t, float *, float *, cudaStream_t);
 int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
 int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
 int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
@@ -112,13 +114,13 @@ int aesmc_smc_step_ws_f32(const float *lp_a, const float *lp_b, const float *lp_
                            workspace_bytes, S(stream));
 }
 
-int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
-                          const float *params_host, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
-                          uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
-                          float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream)
+static int smc_step_lg_common(const char *fn, const float *x_prev, const float *y, const float *noise, const float *q_off,
+                              const float *params_host, const float *params_dev, float half_log_2pi, uint64_t seed,
+                              const uint64_t *seed_dev, uint64_t stream_offset, int64_t B, int64_t K, const double *u,
+                              float *x_new, float *log_w, float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode,
+                              void *stream)
 {
-    const char *fn = "aesmc_smc_step_lg_f32";
-    REQUIRE(y && params_host && flags, fn);
+    REQUIRE(y && (params_host || params_dev) && flags, fn);
     REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= kMaxDim, fn);
     REQUIRE(mode == AESMC_MODE_EXACT || mode == AESMC_MODE_FAST, fn);
     REQUIRE(idx == nullptr || x_out != nullptr, fn); // ancestors may be dropped (idx NULL), the resampled latents not
@@ -132,9 +134,42 @@ int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *nois
                            reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(x_out);
     REQUIRE((bits & 15) == 0, fn);
     if (B == 0) return AESMC_OK;
-    return launch_smc_step_lg(x_prev, y, noise, q_off, params_host, half_log_2pi, seed,
+    return launch_smc_step_lg(x_prev, y, noise, q_off, params_host, params_dev, half_log_2pi, seed,
                               reinterpret_cast<const unsigned long long *>(seed_dev), stream_offset, B, K, u, x_new, log_w,
                               lse, idx, x_out, flags, mode, S(stream));
+}
+
+int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
+                          const float *params_host, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
+                          uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
+                          float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream)
+{
+    REQUIRE(params_host, "aesmc_smc_step_lg_f32");
+    return smc_step_lg_common("aesmc_smc_step_lg_f32", x_prev, y, noise, q_off, params_host, nullptr, half_log_2pi, seed,
+                              seed_dev, stream_offset, B, K, u, x_new, log_w, lse, idx, x_out, flags, mode, stream);
+}
+
+int aesmc_smc_step_lg_dev_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
+                              const float *params_dev, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
+                              uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
+                              float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream)
+{
+    REQUIRE(params_dev, "aesmc_smc_step_lg_dev_f32");
+    return smc_step_lg_common("aesmc_smc_step_lg_dev_f32", x_prev, y, noise, q_off, nullptr, params_dev, half_log_2pi, seed,
+                              seed_dev, stream_offset, B, K, u, x_new, log_w, lse, idx, x_out, flags, mode, stream);
+}
+
+int aesmc_lg_step_bwd_f32(const float *x, const float *x_prev, const float *y, const float *q_off, const float *params_dev,
+                          const float *lse, const float *g_lse, const float *g_next, const int32_t *idx, int64_t B,
+                          int64_t K, float *g_x_prev, float *g_params, void *stream)
+{
+    const char *fn = "aesmc_lg_step_bwd_f32";
+    REQUIRE(x && y && params_dev && lse && g_lse && g_params, fn);
+    REQUIRE((g_next == nullptr) == (idx == nullptr), fn);
+    REQUIRE((x_prev == nullptr) == (g_x_prev == nullptr), fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K <= 16384, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_lg_step_bwd(x, x_prev, y, q_off, params_dev, lse, g_lse, g_next, idx, B, K, g_x_prev, g_params, S(stream));
 }
 
 int aesmc_resample_from_weights_f32(const float *w, const double *u, int64_t B, int64_t K, int32_t *idx,

@@ -8,6 +8,19 @@ namespace aesmc {
 
 struct LgAffine { float mult, off, scale, two_var, log_scale; }; // loc = mult * x + off; 2 var and log scale precomputed by torch
 
+// 5 consecutive floats of a parameter block in DEVICE memory (training: the parameters change every step and are
+// never copied to the host; the block is tiny and stays in L1)
+__device__ __forceinline__ LgAffine lg_load_affine(const float *q)
+{
+    LgAffine a;
+    a.mult = __ldg(q); a.off = __ldg(q + 1); a.scale = __ldg(q + 2); a.two_var = __ldg(q + 3); a.log_scale = __ldg(q + 4);
+    return a;
+}
+__device__ __forceinline__ bool lg_same(const LgAffine &a, const LgAffine &b)
+{
+    return a.mult == b.mult && a.off == b.off && a.scale == b.scale && a.two_var == b.two_var && a.log_scale == b.log_scale;
+}
+
 // Philox4x32-10 counter-based generator (Salmon et al. 2011): 4 x 32 random bits per (key, counter).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
 {

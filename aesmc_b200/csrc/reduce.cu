@@ -458,8 +458,15 @@ static unsigned flat_grid(int64_t n, int threads)
     return (unsigned)blocks;
 }
 
+// row_stats.cu: one warp per row, single pass (used when there are enough rows to fill the machine)
+bool row_stats_warp_supported(const void *lw, const void *x, int64_t B, int64_t K);
+int launch_logsumexp_warp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
+int launch_log_ess_warp_f32(const float *, int64_t, int64_t, float *, cudaStream_t);
+int launch_weighted_moments_warp_f32(const float *, const float *, int64_t, int64_t, float *, float *, cudaStream_t);
+
 int launch_logsumexp_f32(const float *lw, int64_t B, int64_t K, float *lse, int32_t *flags, cudaStream_t st)
 {
+    if (row_stats_warp_supported(lw, nullptr, B, K)) return launch_logsumexp_warp_f32(lw, B, K, lse, flags, st);
     const int t = row_threads(K);
     logsumexp_rows_kernel<float><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, lse, flags);
     count_launch();
@@ -481,6 +488,7 @@ int launch_lognormexp_f32(const float *lw, int64_t B, int64_t K, float *out, int
 }
 int launch_log_ess_f32(const float *lw, int64_t B, int64_t K, float *out, cudaStream_t st)
 {
+    if (row_stats_warp_supported(lw, nullptr, B, K)) return launch_log_ess_warp_f32(lw, B, K, out, st);
     const int t = row_threads(K);
     log_ess_kernel<float><<<row_grid(B, t), t, 0, st>>>(lw, (int)B, (int)K, out);
     count_launch();
@@ -516,6 +524,7 @@ int launch_is_accumulate_f32(const float *a, const float *b, const float *c, flo
 int launch_weighted_moments_f32(const float *x, const float *lw, int64_t B, int64_t K, int64_t D, float *mean,
                                 float *second, cudaStream_t st)
 {
+    if (D == 1 && row_stats_warp_supported(lw, x, B, K)) return launch_weighted_moments_warp_f32(x, lw, B, K, mean, second, st);
     const int t = row_threads(K);
     weighted_moments_kernel<<<row_grid(B, t), t, 0, st>>>(x, lw, (int)B, (int)K, (int)D, mean, second);
     count_launch();

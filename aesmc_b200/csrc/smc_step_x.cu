@@ -197,9 +197,13 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             // propose x ~ q(. | x_prev, y), then log_w = (log p(x | x_prev) + log p(y | x)) - log q(x | x_prev, y), each
             // term with torch.distributions.Normal's float32 arithmetic (lg_model.cuh)
             const float yv = p.y[row];
-            const float qoff = p.q_off ? p.q_off[row] : p.q.off;
+            const LgAffine mt = p.params_dev ? lg_load_affine(p.params_dev) : p.t;
+            const LgAffine me = p.params_dev ? lg_load_affine(p.params_dev + 5) : p.e;
+            const LgAffine mq = p.params_dev ? lg_load_affine(p.params_dev + 10) : p.q;
+            const bool q_same_t = p.params_dev ? (p.q_off == nullptr && lg_same(mq, mt)) : (p.q_same_t != 0);
+            const float qoff = p.q_off ? p.q_off[row] : mq.off;
             const unsigned long long seed = p.seed_dev ? *p.seed_dev : p.seed;
-            const float rcp_t = refined_rcp(p.t.two_var), rcp_e = refined_rcp(p.e.two_var), rcp_q = refined_rcp(p.q.two_var);
+            const float rcp_t = refined_rcp(mt.two_var), rcp_e = refined_rcp(me.two_var), rcp_q = refined_rcp(mq.two_var);
             const float4 *__restrict__ xp4 = p.x_prev ? reinterpret_cast<const float4 *>(p.x_prev + off) + gc : nullptr;
             const float4 *__restrict__ nz4 = p.noise ? reinterpret_cast<const float4 *>(p.noise + off) + gc : nullptr;
 #pragma unroll
@@ -211,14 +215,14 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 float xo[4], lo[4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const f32x2 loc_q = add2(mul2_sep(xs2[h], p.q.mult), splat2(qoff));
-                    const f32x2 x2 = add2(loc_q, mul2_sep(es2[h], p.q.scale)); // Normal.rsample
-                    const f32x2 lq = normal_log_prob2(x2, loc_q, p.q.two_var, rcp_q, p.q.log_scale, p.half_log_2pi);
-                    const f32x2 lt = p.q_same_t ? lq
-                                   : normal_log_prob2(x2, add2(mul2_sep(xs2[h], p.t.mult), splat2(p.t.off)),
-                                                      p.t.two_var, rcp_t, p.t.log_scale, p.half_log_2pi);
-                    const f32x2 le = normal_log_prob2(splat2(yv), add2(mul2_sep(x2, p.e.mult), splat2(p.e.off)),
-                                                      p.e.two_var, rcp_e, p.e.log_scale, p.half_log_2pi);
+                    const f32x2 loc_q = add2(mul2_sep(xs2[h], mq.mult), splat2(qoff));
+                    const f32x2 x2 = add2(loc_q, mul2_sep(es2[h], mq.scale)); // Normal.rsample
+                    const f32x2 lq = normal_log_prob2(x2, loc_q, mq.two_var, rcp_q, mq.log_scale, p.half_log_2pi);
+                    const f32x2 lt = q_same_t ? lq
+                                   : normal_log_prob2(x2, add2(mul2_sep(xs2[h], mt.mult), splat2(mt.off)),
+                                                      mt.two_var, rcp_t, mt.log_scale, p.half_log_2pi);
+                    const f32x2 le = normal_log_prob2(splat2(yv), add2(mul2_sep(x2, me.mult), splat2(me.off)),
+                                                      me.two_var, rcp_e, me.log_scale, p.half_log_2pi);
                     unpack2(x2, xo[2 * h], xo[2 * h + 1]);
                     unpack2(sub2(add2(lt, le), lq), lo[2 * h], lo[2 * h + 1]);
                 }

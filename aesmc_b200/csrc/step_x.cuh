@@ -23,6 +23,7 @@ struct XStepParams {
     const float *q_off;   // [B] per-row proposal offset (observation-dependent), NULL -> q.off
     float *x_new;         // [B,K] out, the newly proposed latents (nullable)
     LgAffine t, e, q;     // transition | initial, emission, proposal
+    const float *params_dev; // non-NULL: the same 15 floats (t | e | q) are read from DEVICE memory instead
     float half_log_2pi;
     int q_same_t;         // proposal == transition (bootstrap): log q is the same number as log p(x | x_prev)
     unsigned long long seed, stream_offset;

@@ -9,8 +9,12 @@ elementwise kernels per time step.
 ``ScalarLinearGaussianSSM`` is an ordinary user model: ``.initial / .transition / .emission / .proposal``
 are callables with the reference's conventions returning torch.distributions, so the same object runs
 through the generic path, through the oracle port and through the reference itself.  ``inference.infer``
-recognises the four bound methods of one instance and -- when no gradient is required -- dispatches to
-``infer_fused``: same arguments, same result dict.  The kernel reproduces torch.distributions.Normal's
+recognises the four bound methods of one instance (or four reference-style modules tied together with
+``link``) and dispatches to ``infer_fused``: same arguments, same result dict.  When gradients are required and only
+the log-evidence is requested -- exactly what ``losses.get_loss`` asks for -- the step kernels run under one
+autograd node whose backward is ONE launch per time step (aesmc_lg_step_bwd_f32: logsumexp gradient, the
+ancestral gather's scatter-add and the analytic Normal gradients); anything else that needs gradients takes the
+differentiable generic path.  The kernel reproduces torch.distributions.Normal's
 float32 arithmetic operation for operation, so with injected noise the fused and the eager path agree
 bit for bit (tests/test_fused_gpu.py); without, noise comes from an in-kernel Philox4x32-10 stream
 seeded from torch's global generator.
@@ -71,6 +75,32 @@ class ScalarLinearGaussianSSM:
     def requires_grad(self):
         return any(t.requires_grad for t in self.tensors())
 
+    def scales_require_grad(self):
+        scales = [self.s0, self.sx, self.sy] + ([self.prop["p0_scale"], self.prop["pt_scale"]] if self.prop is not None else [])
+        return any(t.requires_grad for t in scales)
+
+    def differentiable_parameters(self):
+        """The ten multipliers / offsets the fused backward differentiates, in the order _FusedEvidence expects
+        (proposal entries are placeholders for a bootstrap model)."""
+        z = torch.zeros((), dtype=torch.float32, device=self.m0.device)
+        pr = self.prop or {}
+        return [self.m0, self.a, self.b, self.c, self.d, pr.get("p0_y", z), pr.get("p0_off", z), pr.get("pt_x", z),
+                pr.get("pt_y", z), pr.get("pt_off", z)]
+
+    def kernel_params_device(self):
+        """float32 [2, 15] ON THE DEVICE (no host round trip; row 0 for t = 0, row 1 for t >= 1; each row t | e | q)."""
+        with torch.no_grad():
+            zero = torch.zeros_like(self.m0)
+            init = self._affine(zero, self.m0, self.s0)
+            trans = self._affine(self.a, self.b, self.sx)
+            emis = self._affine(self.c, self.d, self.sy)
+            if self.prop is None:
+                q0, qt = init, trans
+            else:
+                q0 = self._affine(zero, self.prop["p0_off"], self.prop["p0_scale"])
+                qt = self._affine(self.prop["pt_x"], self.prop["pt_off"], self.prop["pt_scale"])
+            return torch.stack([torch.cat([init, emis, q0]), torch.cat([trans, emis, qt])]).float().contiguous()
+
     # ---- parameters for the fused kernel -------------------------------------------------------------
     def _affine(self, mult, off, scale):
         # (mult, off, scale, 2*var, log scale) computed with torch on the model's device, exactly as
@@ -99,8 +129,69 @@ class ScalarLinearGaussianSSM:
         return (observation * self.prop["pt_y"] + self.prop["pt_off"]).contiguous()
 
 
+class LinkedLGSSM(ScalarLinearGaussianSSM):
+    """A ScalarLinearGaussianSSM VIEW of four reference-style callables (the reference's test/models/lgssm.py:10-72
+    and this repo's tests/models/lgssm.py): Initial(loc, scale); Transition / Emission modules with a scalar
+    Parameter ``mult`` and a constant ``scale``; a Proposal module with ``lin_0 = Linear(1, 1)``,
+    ``lin_t = Linear(2, 1)`` on (x_prev, y_t) and constant ``scale_0`` / ``scale_t``.  Parameters are read from the
+    modules at every call, so optimiser updates are seen and gradients land on the modules' own Parameters."""
+
+    def __init__(self, initial, transition, emission, proposal, proposal_scale_t=None):
+        self._mods = (initial, transition, emission, proposal)
+        self.device = transition.mult.device
+        self._scale_t_attr = proposal_scale_t
+
+    def _f(self, v):
+        if torch.is_tensor(v):
+            return v.to(device=self.device, dtype=torch.float32).reshape(())
+        return torch.tensor(float(v), dtype=torch.float32, device=self.device)
+
+    m0 = property(lambda s: s._f(s._mods[0].loc))
+    s0 = property(lambda s: s._f(s._mods[0].scale))
+    a = property(lambda s: s._mods[1].mult.reshape(()))
+    b = property(lambda s: s._f(0.0))
+    sx = property(lambda s: s._f(s._mods[1].scale))
+    c = property(lambda s: s._mods[2].mult.reshape(()))
+    d = property(lambda s: s._f(0.0))
+    sy = property(lambda s: s._f(s._mods[2].scale))
+
+    @property
+    def prop(self):
+        q = self._mods[3]
+        scale_t = q.scale_t if self._scale_t_attr is None else self._scale_t_attr
+        return {"p0_y": q.lin_0.weight[0, 0], "p0_off": q.lin_0.bias[0], "p0_scale": self._f(q.scale_0),
+                "pt_x": q.lin_t.weight[0, 0], "pt_y": q.lin_t.weight[0, 1], "pt_off": q.lin_t.bias[0],
+                "pt_scale": self._f(scale_t)}
+
+
+def link(initial, transition, emission, proposal, proposal_scale_t=None):
+    """Opt reference-style LGSSM modules into the fused kernels: checks their structure and ties them together, so
+    that ``infer`` / ``get_loss`` called with exactly these four objects run (and train) through
+    aesmc_smc_step_lg_* instead of torch elementwise kernels.  Returns the LinkedLGSSM view.
+    proposal_scale_t: the scale the proposal's forward() really uses for t >= 1 (the reference's own
+    test/models/lgssm.py:63 passes scale_0 there); default proposal.scale_t."""
+    import torch.nn as nn
+    ok = (hasattr(initial, "loc") and hasattr(initial, "scale")
+          and isinstance(getattr(transition, "mult", None), torch.Tensor) and hasattr(transition, "scale")
+          and isinstance(getattr(emission, "mult", None), torch.Tensor) and hasattr(emission, "scale")
+          and isinstance(getattr(proposal, "lin_0", None), nn.Linear) and isinstance(getattr(proposal, "lin_t", None), nn.Linear)
+          and hasattr(proposal, "scale_0") and hasattr(proposal, "scale_t"))
+    if not ok or tuple(proposal.lin_0.weight.shape) != (1, 1) or tuple(proposal.lin_t.weight.shape) != (1, 2) \
+            or transition.mult.numel() != 1 or emission.mult.numel() != 1:
+        raise ValueError("link() needs Initial(loc, scale), Transition/Emission modules with a scalar `mult` Parameter and a "
+                         "`scale`, and a Proposal with lin_0 = Linear(1, 1), lin_t = Linear(2, 1), scale_0, scale_t")
+    view = LinkedLGSSM(initial, transition, emission, proposal, proposal_scale_t)
+    proposal._aesmc_b200_fused = view
+    return view
+
+
 def model_of(initial, transition, emission, proposal):
-    """The ScalarLinearGaussianSSM whose bound methods these four callables are, else None."""
+    """The ScalarLinearGaussianSSM whose bound methods these four callables are (or the LinkedLGSSM view that
+    ``link`` tied to exactly these four objects), else None."""
+    view = getattr(proposal, "_aesmc_b200_fused", None)
+    if isinstance(view, LinkedLGSSM):
+        return view if view._mods == (initial, transition, emission, proposal) or all(
+            a is b for a, b in zip(view._mods, (initial, transition, emission, proposal))) else None
     owner = getattr(proposal, "__self__", None)
     if not isinstance(owner, ScalarLinearGaussianSSM):
         return None
@@ -110,7 +201,9 @@ def model_of(initial, transition, emission, proposal):
     return owner
 
 
-def applicable(model, observations, num_particles):
+def applicable(model, observations, num_particles, evidence_only=False):
+    """Can this call run on the fused kernels?  evidence_only: the caller wants nothing but the log-evidence
+    (get_loss) -- the one request the fused path can differentiate."""
     if model is None or not torch.cuda.is_available():
         return False
     first = observations[0]
@@ -118,9 +211,13 @@ def applicable(model, observations, num_particles):
         return False
     if first.dtype != torch.float32 or model.m0.device != first.device:
         return False
+    if not (64 <= num_particles <= 16384 and num_particles % 4 == 0):
+        return False
     if torch.is_grad_enabled() and model.requires_grad():
-        return False  # infer_fused has no autograd: a trainable model takes the differentiable generic path
-    return 64 <= num_particles <= 16384 and num_particles % 4 == 0
+        # trainable model: fused only for the evidence, and only with constant scales (the backward kernel
+        # differentiates multipliers and offsets); everything else takes the differentiable generic path
+        return evidence_only and not model.scales_require_grad()
+    return True
 
 
 _HALF_LOG_2PI = float(np.float32(math.log(math.sqrt(2 * math.pi))))
@@ -196,6 +293,87 @@ def infer_fused(model, observations, num_particles, return_log_marginal_likeliho
     if check_finite:
         _ops.raise_on_flags(flags)
     return result
+
+
+class _FusedEvidence(torch.autograd.Function):
+    """log-evidence [B] of the SMC filter on a scalar linear-Gaussian model, differentiable w.r.t. the model's ten
+    multipliers / offsets: T fused-step launches forward, T aesmc_lg_step_bwd_f32 launches backward.  Replaces the
+    autograd graph that losses.get_loss builds over inference.py:85-134 (~60 torch kernels per time step)."""
+
+    @staticmethod
+    def forward(ctx, obs, q_off, params_dev, u_all, noise, num_particles, mode, seed, flags, bootstrap, *theta):
+        T, B = obs.shape
+        K, dev = num_particles, obs.device
+        X = torch.empty(T, B, K, dtype=torch.float32, device=dev)                 # proposed latents x_t
+        XP = torch.empty(max(T - 1, 1), B, K, dtype=torch.float32, device=dev)    # XP[t] = x_t[idx_t]: inputs of step t + 1
+        IDX = torch.empty(max(T - 1, 1), B, K, dtype=torch.int32, device=dev)
+        lses = torch.empty(T, B, dtype=torch.float32, device=dev)
+        for t in range(T):
+            last = t == T - 1
+            _lib.call("aesmc_smc_step_lg_dev_f32", _lib.ptr(XP[t - 1]) if t else None, _lib.ptr(obs[t]),
+                      _lib.ptr(noise[t]) if noise is not None else None, _lib.ptr(q_off[t]) if q_off is not None else None,
+                      _lib.ptr(params_dev[0 if t == 0 else 1]), _HALF_LOG_2PI, seed, None, t, B, K,
+                      None if last else _lib.ptr(u_all[t]), _lib.ptr(X[t]), None, _lib.ptr(lses[t]),
+                      None if last else _lib.ptr(IDX[t]), None if last else _lib.ptr(XP[t]), _lib.ptr(flags), mode)
+        ctx.save_for_backward(obs, q_off, params_dev, X, XP, IDX, lses)
+        ctx.bootstrap = bootstrap
+        return (lses - math.log(K)).sum(dim=0)  # inference.py:130-132
+
+    @staticmethod
+    def backward(ctx, g_lml):
+        obs, q_off, params_dev, X, XP, IDX, lses = ctx.saved_tensors
+        T, B, K = X.shape
+        dev = X.device
+        g_lse = g_lml.contiguous().float()  # d lml / d lse_t = 1 for every t
+        gpar = torch.empty(T, B, 6, dtype=torch.float32, device=dev)
+        G = None
+        for t in range(T - 1, -1, -1):
+            g_xp = torch.empty(B, K, dtype=torch.float32, device=dev) if t else None
+            _lib.call("aesmc_lg_step_bwd_f32", _lib.ptr(X[t]), _lib.ptr(XP[t - 1]) if t else None, _lib.ptr(obs[t]),
+                      _lib.ptr(q_off[t]) if q_off is not None else None, _lib.ptr(params_dev[0 if t == 0 else 1]),
+                      _lib.ptr(lses[t]), _lib.ptr(g_lse), _lib.ptr(G) if G is not None else None,
+                      _lib.ptr(IDX[t]) if t < T - 1 else None, B, K, _lib.ptr(g_xp), _lib.ptr(gpar[t]))
+            G = g_xp
+        P = gpar.sum(dim=1)                       # [T, 6]: t.mult, t.off, e.mult, e.off, q.mult, q_off
+        Pt = P[1:].sum(dim=0) if T > 1 else torch.zeros(6, device=dev)
+        gq = gpar[:, :, 5]                        # [T, B] dL/dq_off[t, b]
+        g_m0, g_a, g_b = P[0, 1], Pt[0], Pt[1]
+        g_c, g_d = P[:, 2].sum(), P[:, 3].sum()
+        zero = torch.zeros((), device=dev)
+        if ctx.bootstrap:  # the proposal IS the prior: its reparameterised path lands on the prior's parameters
+            g_m0 = g_m0 + gq[0].sum()
+            g_a, g_b = g_a + Pt[4], g_b + Pt[5]
+            g_p0y = g_p0o = g_ptx = g_pty = g_pto = zero
+        else:
+            g_p0y, g_p0o = (gq[0] * obs[0]).sum(), gq[0].sum()
+            g_ptx = Pt[4]
+            g_pty, g_pto = ((gq[1:] * obs[1:]).sum(), gq[1:].sum()) if T > 1 else (zero, zero)
+        return (None,) * 10 + (g_m0, g_a, g_b, g_c, g_d, g_p0y, g_p0o, g_ptx, g_pty, g_pto)
+
+
+def evidence_with_grad(model, observations, num_particles, uniforms=None, resampling_mode=None, check_finite=True,
+                       noise=None):
+    """Differentiable SMC log-evidence [B] of a (trainable) scalar linear-Gaussian model on the fused kernels."""
+    T = len(observations)
+    obs = observations if torch.is_tensor(observations) else torch.stack(list(observations))
+    obs = obs.contiguous()
+    B, K, dev = obs.shape[1], num_particles, obs.device
+    flags = _ops.new_flags(dev)
+    u_all = None
+    if T > 1:
+        u_all = _ops.uniforms_table_to_device(np.random.uniform(size=[T - 1, B]) if uniforms is None else uniforms, T - 1, B, dev)
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    q_off = None
+    if model.prop is not None:
+        with torch.no_grad():
+            pr = model.prop
+            q_off = torch.cat([(obs[:1] * pr["p0_y"] + pr["p0_off"]), (obs[1:] * pr["pt_y"] + pr["pt_off"])]).contiguous()
+    nz = None if noise is None else (noise if torch.is_tensor(noise) else torch.stack(list(noise))).contiguous()
+    lml = _FusedEvidence.apply(obs, q_off, model.kernel_params_device(), u_all, nz, K, _ops.mode_code(resampling_mode),
+                               seed, flags, model.prop is None, *model.differentiable_parameters())
+    if check_finite:
+        _ops.raise_on_flags(flags)
+    return lml
 
 
 class GraphedFilter:

@@ -121,7 +121,16 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
         # models of the fused family (aesmc_b200.fused) run with their sampling and log-densities inside
         # the step kernel; everything else takes the generic path below
         model = fused.model_of(initial, transition, emission, proposal) if _allow_fused else None
-        if model is not None and fused.applicable(model, observations, K):
+        evidence_only = return_log_marginal_likelihood and not (
+            return_latents or return_original_latents or return_log_weight or return_log_weights or return_ancestral_indices)
+        if model is not None and fused.applicable(model, observations, K, evidence_only):
+            if torch.is_grad_enabled() and model.requires_grad():
+                # training (losses.get_loss): forward and backward on the fused kernels, one launch per time step each
+                result = dict.fromkeys(("log_marginal_likelihood", "latents", "original_latents", "log_weight",
+                                        "log_weights", "ancestral_indices", "last_latent"))
+                result["log_marginal_likelihood"] = fused.evidence_with_grad(
+                    model, observations, K, uniforms=uniforms, resampling_mode=resampling_mode, check_finite=check_finite)
+                return result
             return fused.infer_fused(model, observations, K, return_log_marginal_likelihood, return_latents,
                                      return_original_latents, return_log_weight, return_log_weights,
                                      return_ancestral_indices, uniforms=uniforms, resampling_mode=resampling_mode,

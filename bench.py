@@ -295,7 +295,7 @@ def run_native(args):
         torch.cuda.empty_cache()
         ctx = {"rank": rank, "world": world, "dev": dev, "mode": mode, "K": K, "T": T, "B": B}
         for name, fn in (("parity", leg_parity), ("strong", leg_strong), ("sweep_c5", leg_sweep_c5),
-                         ("train_c4", leg_train_c4)):
+                         ("train_c4", leg_train_c4), ("train_lgssm", leg_train_lgssm)):
             try:
                 extras[name] = fn(ctx, ring, arena, u, value, ms_per_step)
             except Exception as exc:  # an extra leg must never take the headline line down with it
@@ -566,6 +566,56 @@ def leg_train_c4(ctx, ring, arena, u, value, ms_per_step):
             "allreduce_us": ar_us, "allreduce_floats": int(flat.numel()), "replicas_in_sync": in_sync,
             "value": Bl * world * K * T / (ms * 1e-3), "unit": UNIT, "scaling": "weak"}
 
+
+
+def leg_train_lgssm(ctx, ring, arena, u, value, ms_per_step):
+    """AESMC training of the reference's own trainable LGSSM (test/models/lgssm.py:19-72: learnable transition /
+    emission multipliers, two-Linear proposal) at B = 1024 rows per rank, K = 4096, T = 50: one optimiser step =
+    get_loss('aesmc') forward + backward (+ gradient all-reduce at N > 1) + Adam.  `fused`: the modules linked to the
+    fused kernels (aesmc_b200.fused.link: T forward + T backward launches); `generic`: the same modules through
+    torch-eager callables and torch autograd around the step kernel."""
+    from aesmc_b200 import distributed, fused, losses
+    from tests.models import lgssm
+    world, dev, rank = ctx["world"], ctx["dev"], ctx["rank"]
+    B, K, T = 1024, 4096, 50
+    torch.distributions.Distribution.set_default_validate_args(False)
+    obs = torch.from_numpy(lgssm.simulate(T, B, A=0.9, Q=1.0, C=1.0, R=0.25, seed=50 + rank)).to(dev)
+    obs_list = [obs[t] for t in range(T)]
+    out = {"model": "reference-style trainable LGSSM (learnable multipliers, Linear(1,1) / Linear(2,1) proposal), 'aesmc' loss + Adam",
+           "rows_per_rank": B, "rows_total": B * world, "K": K, "T": T, "unit_ms": "ms per optimiser step"}
+    for label, link in (("fused", True), ("generic", False)):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        init, trans, emis, prop = (lgssm.Initial(0.0, 1.0), lgssm.Transition(0.5, 1.0).to(dev), lgssm.Emission(0.5, 0.5).to(dev),
+                                   lgssm.Proposal(0.9, 0.9).to(dev))
+        if link:
+            fused.link(init, trans, emis, prop)
+        params = [q for m in (trans, emis, prop) for q in m.parameters()]
+        opt = torch.optim.Adam(params, lr=1e-3)
+
+        def step():
+            opt.zero_grad()
+            loss = losses.get_loss(obs_list, K, "aesmc", init, trans, emis, prop)
+            loss.backward()
+            if world > 1:
+                distributed.all_reduce_gradients(params, B, B * world)
+            opt.step()
+            return loss
+
+        for _ in range(2):
+            step()
+        reps = 5 if link else 3
+        ms = _event_time_ms(step, reps, world, dev)
+        out[label + "_ms"] = ms
+        out[label + "_value"] = B * world * K * T / (ms * 1e-3)
+        del init, trans, emis, prop, params, opt
+        torch.cuda.empty_cache()
+    out["speedup_fused_over_generic"] = out["generic_ms"] / out["fused_ms"]
+    out["unit"] = UNIT
+    # forward + backward of the fused path move 16 + 20 bytes per particle-step (DESIGN.md section 3.5)
+    peak, _ = load_peaks()
+    out["fused_frac_of_measured_hbm"] = round(36.0 * B * K * T / (out["fused_ms"] * 1e-3) / 1e9 / peak, 4)
+    return out
 
 
 def time_oracle_core(K, T, D, rows):

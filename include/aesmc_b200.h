@@ -105,6 +105,28 @@ int aesmc_smc_step_lg_f32(const float *x_prev, const float *y, const float *nois
                           uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
                           float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream);
 
+/* The same step with the 15 model parameters read from DEVICE memory (training: the parameters change every
+ * optimiser step and never visit the host, so the whole step can also be captured in a CUDA graph). */
+int aesmc_smc_step_lg_dev_f32(const float *x_prev, const float *y, const float *noise, const float *q_off,
+                              const float *params_dev, float half_log_2pi, uint64_t seed, const uint64_t *seed_dev,
+                              uint64_t stream_offset, int64_t B, int64_t K, const double *u, float *x_new, float *log_w,
+                              float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream);
+
+/*
+ * Backward of one fused linear-Gaussian step: replaces torch autograd of losses.get_loss(..., 'aesmc')
+ * (losses.py:5-65 -> inference.py:99-134) for that model family -- the logsumexp gradient, the ancestral
+ * gather's scatter-add over descendants (state.py:158-183 backward) and the analytic Normal.log_prob /
+ * rsample gradients in one launch per time step.
+ *   x, x_prev [B,K]: the step's proposed latents and its (resampled) inputs (x_prev NULL at t = 0, then g_x_prev NULL)
+ *   lse, g_lse [B]: the step's log-normaliser and dL/dlse;  params_dev: the 15 floats of the forward step
+ *   g_next [B,K], idx [B,K]: dL/d(resampled latents) of the NEXT step and this step's ancestors (both NULL at t = T-1)
+ *   g_x_prev [B,K] out: dL/dx_prev;  g_params [B,6] out: per-row sums for
+ *   (t.mult, t.off, e.mult, e.off, q.mult, q_off[b]); scales are treated as constants.  K <= 16384.
+ */
+int aesmc_lg_step_bwd_f32(const float *x, const float *x_prev, const float *y, const float *q_off,
+                          const float *params_dev, const float *lse, const float *g_lse, const float *g_next,
+                          const int32_t *idx, int64_t B, int64_t K, float *g_x_prev, float *g_params, void *stream);
+
 /*
  * Resampling entered at a later stage (used by the staged parity tests, and useful on their own):
  *   from normalised weights w [B,K]: cumulative sum (inference.py:257), renormalisation by the last

@@ -147,3 +147,119 @@ def test_graphed_filter_fresh_randomness_and_kalman(cuda):
     small = fused.GraphedFilter(model, 50, 1, 100)
     out = small(torch.from_numpy(ys[:, :1]))
     assert out.shape == (1,) and torch.isfinite(out).all()
+
+
+# ---- training through the fused kernels (aesmc_lg_step_bwd_f32) -------------------------------------------------
+def _port_loss_and_grads(obs_np, K, u, seed):
+    """losses.get_loss('aesmc') of the CPU oracle port (the reference's algorithm, torch autograd) on the
+    reference-style trainable LGSSM, Normal.rsample fed from torch.Generator(seed); returns (loss, grads, noise)."""
+    import torch.distributions.normal as tdn
+    from oracle import reference_port as port
+    torch.manual_seed(0)
+    mods = (lgssm.Initial(0.1, 1.2), lgssm.Transition(0.8, 0.9), lgssm.Emission(1.1, 0.6), lgssm.Proposal(0.8, 0.7))
+    gen = torch.Generator().manual_seed(seed)
+    drawn = []
+    orig = tdn._standard_normal
+
+    def fake(shape, dtype, device):
+        z = torch.randn(tuple(shape), generator=gen, dtype=dtype)
+        drawn.append(z)
+        return z.to(device)
+
+    tdn._standard_normal = fake
+    try:
+        loss = port.get_loss([torch.from_numpy(o) for o in obs_np], K, "aesmc", *mods, uniforms=u)
+    finally:
+        tdn._standard_normal = orig
+    loss.backward()
+    grads = [p.grad.clone() for m in mods[1:] for p in m.parameters()]
+    B = obs_np.shape[1]
+    noise = torch.stack([z if tuple(z.shape) == (B, K) else z.t().contiguous() for z in drawn])  # t = 0 is drawn [K, B]
+    return loss.item(), grads, noise, mods
+
+
+@pytest.mark.parametrize("K,T,B", [(256, 6, 4), (1024, 5, 3)])
+def test_fused_training_gradients_match_reference_port(cuda, K, T, B):
+    """get_loss('aesmc') through the fused forward + backward kernels against the oracle port (CPU, torch autograd
+    over the reference's algorithm) on identical noise and uniforms: loss within 1e-5, every parameter gradient of
+    the reference's trainable LGSSM (test/models/lgssm.py:19-72) within 1e-4 relative."""
+    obs_np = lgssm.simulate(T, B, seed=4)
+    u = np.random.default_rng(5).random((T - 1, B))
+    ref_loss, ref_grads, noise, _ = _port_loss_and_grads(obs_np, K, u, seed=6)
+    torch.manual_seed(0)
+    init, trans, emis, prop = (lgssm.Initial(0.1, 1.2), lgssm.Transition(0.8, 0.9).to(cuda), lgssm.Emission(1.1, 0.6).to(cuda),
+                               lgssm.Proposal(0.8, 0.7).to(cuda))
+    view = fused.link(init, trans, emis, prop)
+    obs = torch.from_numpy(obs_np).to(cuda)
+    assert fused.model_of(init, trans, emis, prop) is view and fused.applicable(view, obs, K, evidence_only=True)
+    assert not fused.applicable(view, obs, K, evidence_only=False)   # other outputs: differentiable generic path
+    lml = fused.evidence_with_grad(view, obs, K, uniforms=u, noise=noise.to(cuda))
+    loss = -lml.mean()
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref_loss, rtol=1e-5)
+    got = [p.grad.cpu() for m in (trans, emis, prop) for p in m.parameters()]
+    for g, r in zip(got, ref_grads):
+        np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=1e-4, atol=2e-6)
+
+
+def test_get_loss_dispatches_linked_modules_to_fused_kernels(cuda):
+    """losses.get_loss with linked reference-style modules: 2 T launches (T forward steps, T backward steps), gradients
+    on the modules' own Parameters, and a few Adam steps reduce the loss on data from the true model."""
+    from aesmc_b200 import losses
+    T, B, K = 10, 32, 512
+    obs = torch.from_numpy(lgssm.simulate(T, B, A=0.9, Q=1.0, C=1.0, R=0.25, seed=3)).to(cuda)
+    torch.manual_seed(1)
+    np.random.seed(1)
+    init, trans, emis, prop = (lgssm.Initial(0.0, 1.0), lgssm.Transition(0.2, 1.0).to(cuda), lgssm.Emission(0.3, 0.5).to(cuda),
+                               lgssm.Proposal(0.9, 0.9).to(cuda))
+    fused.link(init, trans, emis, prop)
+    params = [p for m in (trans, emis, prop) for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=0.05)
+    first = None
+    for it in range(40):
+        opt.zero_grad()
+        n0 = aesmc_b200._lib.launch_count()
+        loss = losses.get_loss([obs[t] for t in range(T)], K, "aesmc", init, trans, emis, prop)
+        assert aesmc_b200._lib.launch_count() - n0 == T
+        loss.backward()
+        assert aesmc_b200._lib.launch_count() - n0 == 2 * T
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+        opt.step()
+        first = loss.item() if first is None else first
+    assert loss.item() < first - 0.5, (first, loss.item())
+    assert abs(trans.mult.item()) > 0.4 and abs(emis.mult.item()) > 0.5      # moving towards (0.9, 1.0)
+
+
+@pytest.mark.parametrize("proposal", ["bootstrap", AFFINE])
+def test_fused_backward_equals_generic_autograd(cuda, proposal):
+    """Same model object, same injected noise and uniforms: the fused forward + backward against this repo's generic
+    path (torch-eager callables + step kernel + torch autograd), including the bootstrap proposal whose
+    reparameterised path lands on the prior's parameters."""
+    import torch.distributions.normal as tdn
+    T, B, K = 6, 4, 256
+    model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device=cuda)
+    names = ["m0", "a", "b", "c", "d"]
+    leaves = [getattr(model, n).requires_grad_() for n in names]
+    if model.prop is not None:
+        for k in ("p0_y", "p0_off", "pt_x", "pt_y", "pt_off"):
+            leaves.append(model.prop[k].requires_grad_())
+    obs = torch.from_numpy(lgssm.simulate(T, B, seed=1)).to(cuda)
+    noise = torch.randn(T, B, K, device=cuda, generator=torch.Generator(device=cuda).manual_seed(0))
+    u = np.random.default_rng(0).random((T - 1, B))
+    lml = fused.evidence_with_grad(model, obs, K, uniforms=u, noise=noise)
+    (-lml.mean()).backward()
+    got = [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    it = iter(noise)
+    orig = tdn._standard_normal
+    tdn._standard_normal = lambda shape, dtype, device: (lambda z: z if tuple(shape) == tuple(z.shape) else z.t().contiguous())(next(it))
+    try:
+        res = inference.infer("smc", obs, *model.callables(), K, return_log_marginal_likelihood=True, return_latents=False,
+                              return_log_weight=False, uniforms=u, _allow_fused=False)
+    finally:
+        tdn._standard_normal = orig
+    assert torch.equal(res["log_marginal_likelihood"], lml.detach())
+    (-res["log_marginal_likelihood"].mean()).backward()
+    for g, t, n in zip(got, leaves, names + ["p0_y", "p0_off", "pt_x", "pt_y", "pt_off"]):
+        np.testing.assert_allclose(g.cpu().numpy(), t.grad.cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=n)

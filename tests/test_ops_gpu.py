@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import aesmc_b200
-from aesmc_b200 import _ops, inference, math as amath, state, statistics
+from aesmc_b200 import _lib, _ops, inference, math as amath, state, statistics
 from oracle import core as oracle
 
 pytestmark = pytest.mark.gpu
@@ -318,3 +318,36 @@ def test_independent_normal_log_prob_fast_path(cuda):
     per_dim = Independent(Normal(loc, torch.rand(D, device=cuda, generator=gen) + 0.5, validate_args=False), 1, validate_args=False)
     assert _ops.independent_normal_log_prob(per_dim, y) is None
     assert torch.equal(state.log_prob(per_dim, y), per_dim.log_prob(y))
+
+
+@pytest.mark.parametrize("K", [4, 64, 1000, 4096, 12000])
+def test_warp_per_row_statistics(cuda, K):
+    """row_stats.cu (one warp per row, single pass, online max / sum): taken when there are >= 4 rows per SM.
+    logsumexp, log-ESS and the weighted moments against float64 references, incl. -inf entries, an all -inf row,
+    a +inf row, a NaN row and a row with one dominant particle."""
+    B = 1200
+    rng = np.random.default_rng(K)
+    lw = (rng.standard_normal((B, K)) * rng.uniform(0.3, 15.0, (B, 1))).astype(np.float32)
+    lw[1, ::2] = -np.inf
+    lw[2] = -np.inf
+    lw[3, K // 2] = np.inf
+    lw[4, K // 3] = np.nan
+    lw[5] = -80.0
+    lw[5, K - 1] = 30.0
+    lw[6] = 0.25
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    t, tx = torch.from_numpy(lw).to(cuda), torch.from_numpy(x).to(cuda)
+    flags = _ops.new_flags(cuda)
+    lse = _ops.logsumexp_rows(t, flags).cpu().numpy()
+    ok = np.ones(B, bool)
+    ok[[2, 3, 4]] = False
+    np.testing.assert_allclose(lse[ok], oracle.lse_f64(lw[ok]), rtol=2e-6, atol=2e-6)
+    assert np.isneginf(lse[2]) and np.isposinf(lse[3]) and np.isnan(lse[4])
+    assert int(flags.item()) & _lib.FLAG_NAN
+    ess = _ops.log_ess_rows(t).cpu().numpy()
+    np.testing.assert_allclose(ess[ok], oracle.log_ess_f64(lw[ok]), rtol=2e-5, atol=2e-5)
+    assert np.isnan(ess[4])
+    mean, second = _ops.weighted_moments(tx, t)
+    w = torch.softmax(t[ok].double(), dim=1)
+    torch.testing.assert_close(mean[ok, 0].double(), (w * tx[ok].double()).sum(1), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(second[ok, 0].double(), (w * tx[ok].double() ** 2).sum(1), rtol=2e-5, atol=2e-6)
