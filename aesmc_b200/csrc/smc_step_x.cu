@@ -110,7 +110,45 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+// barrier 0 of the CTA, for the one place where the warps reach it on different code paths (warp-uniform branch)
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void sts_b32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// IEEE division out of line (rare paths: keeps eight inlined copies of its range handling out of the instruction cache)
+static __device__ __noinline__ float fdiv_rn_call(float a, float b) { return __fdiv_rn(a, b); }
+
+// the boundary count of common.cuh with the float64 uniform read from shared memory inside the rare fix-up
+static __device__ __noinline__ int count_positions_below_slow_x(float cdf_entry, const double *u_sh, int K)
+{
+    const double Kd = (double)K;
+    return count_positions_below(cdf_entry, *u_sh, K, Kd, Kd * 8.8817841970012523e-16);
+}
+// The boundary count for a CDF entry whose float32 closed form landed within tol32 of an integer (~0.1 % of the
+// particles), without float64 arithmetic.  K is a power of two in this kernel, so T = cdfn K and the reference's
+// pos_k = fl64(u + k) / K < cdfn  <=>  fl64(u + k) < T are exact scalings.  With T = Ti + Tf (integer and fraction,
+// both exact in float32): every k < Ti counts, no k > Ti does, and k = Ti counts iff u < Tf -- unless float64's
+// rounding of u + k interferes, which needs |u - Tf| or 1 - u below K 2^-52.  u = u_hi + u_lo (u_hi = fl32(u),
+// u_lo = fl32(u - u_hi): 2^-50 absolute error), u_hi - Tf is exact whenever the two are close (Sterbenz), so the
+// sign of d = (u_hi - Tf) + u_lo is the sign of u - Tf unless |d| is below a band of K 2^-46; only then (and for
+// u_hi = 1) the reference's own float64 expression is evaluated (count_positions_below_slow_x).
+__device__ __forceinline__ int count_positions_near_x(float cdfn, float u_hi, const float *u_lo_sh, const double *u_sh,
+                                                      int K, float Kf)
+{
+    const float T = __fmul_rn(cdfn, Kf);
+    const float Ti = floorf(T);
+    const float d = __fadd_rn(__fsub_rn(u_hi, __fsub_rn(T, Ti)), *u_lo_sh);
+    if (fabsf(d) > Kf * 1.4210854715202004e-14f && u_hi < 1.0f) return (int)Ti + (d < 0.0f);
+    return count_positions_below_slow_x(cdfn, u_sh, K);
+}
+__device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry, const double *u_sh, const float *u_lo_sh,
+                                                                float u32, int K, float Kf, float tol32)
+{
+    const float tf = __fmaf_rn(cdf_entry, Kf, -u32);
+    const float tm = __fadd_rn(tf, 12582912.0f);
+    const float d = __fsub_rn(tf, __fsub_rn(tm, 12582912.0f)); // tf - rint(tf), exact
+    if (fabsf(d) > tol32) return __float_as_int(tm) - 0x4B400000 + (d > 0.0f); // ceil(tf) <= K
+    return count_positions_near_x(cdf_entry, u32, u_lo_sh, u_sh, K, Kf);
+}
 
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
 __device__ __forceinline__ void compose(int p0, int p1, int n0, int n1, int &h0, int &h1)
@@ -120,11 +158,13 @@ __device__ __forceinline__ void compose(int p0, int p1, int n0, int n1, int &h0,
 }
 
 template <int NW> struct Shared {
+    double u64;               // this row's uniform (read by the rarest fix-up of the boundary count)
+    float ulo;                // u64 - fl32(u64) (read by the rare float32 fix-up)
     float wmax[NW], part[NW], wsum[NW];
-    int cnt[NW], i1[NW], i2[NW];
+    int cnt[NW], nrec[NW], i2[NW];
     float lse, total;
     int bad, fail;
-    float seg_state[NW * 32]; // exact chain value entering each segment, [warp][segment]
+    float seg_state[NW * 32]; // exact chain value [warp][k]: entering the warp's span (k = 0), after its k-th mixed block
 };
 
 template <int NW> __device__ __forceinline__ float across_max(const float *arr, int lane)
@@ -143,9 +183,12 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 #ifndef AESMC_X_REDUNDANT_TAIL
 #define AESMC_X_REDUNDANT_TAIL 0 // 1: every warp evaluates the scalar lse tail itself, no barrier (3) (measured: -1 %)
 #endif
-#ifndef AESMC_X_WALKER_WARP
-#define AESMC_X_WALKER_WARP (NW - 1)
+#ifndef AESMC_X_FORCE_FAIL
+#define AESMC_X_FORCE_FAIL 0 // 1 (test builds): every row fails the scan's verification and takes the sequential redo path
 #endif
+#ifndef AESMC_X_ABLATE
+#define AESMC_X_ABLATE 0 // timing experiments only (WRONG results): bit 0 no mixed-block walk, 1 no level-2 walk at all,
+#endif                   // 2 no lse tail, 3 no float64 fix-up, 4 verification ignored
 
 // ALIAS (plain step with a latent row to gather): the latent row is staged into the weight buffer once the exact
 // scan is done with it -- 36 KB of shared memory per 256-thread CTA instead of 52, so five CTAs fit an SM, and the
@@ -153,7 +196,11 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 // The fused-model step produces the latents itself in P1 and keeps the separate staging row (four CTAs per SM).
 template <bool HAS_X, bool FUSED> struct XConfig {
     static constexpr bool kAlias = HAS_X && !FUSED;
+#ifdef AESMC_X_THREADS_PER_SM
+    static constexpr int kThreadsPerSM = AESMC_X_THREADS_PER_SM;
+#else
     static constexpr int kThreadsPerSM = FUSED ? 1024 : 1280;
+#endif
 };
 
 template <int NT, bool HAS_X, bool FUSED>
@@ -170,8 +217,10 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     float4 *bufX4 = AESMC_X_ALIAS_X ? bufW4 : reinterpret_cast<float4 *>(bufM4 + ROWCH); // staged latent row
     int *bufM = reinterpret_cast<int *>(bufM4);
     const float *bufX = reinterpret_cast<const float *>(bufX4);
-    int4 *seg_rec = bufM4;                                          // [NW][32] (last block, binade, c0, c1): only the
-                                                                    // walker reads it, before the marks are zeroed
+    // [NW][32] records of the exact scan, written by every warp, read by the walker warp: (c0, mixed block's chunk + 1
+    // or 0 | (c1 - c0 + 1) << 16) -- the two entries of a parity map differ by -1, 0 or 1 (two chains that start one
+    // unit apart stay 0, 1 or 2 units apart: round-to-nearest shifts both alike except at ties)
+    int2 *seg_rec = reinterpret_cast<int2 *>(bufM4 + ROWCH + ((HAS_X && !AESMC_X_ALIAS_X) ? NCH : 0));
     __shared__ Shared<NW> sh;
     float *seg_state = sh.seg_state;
 
@@ -188,7 +237,12 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
 
     for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
         const size_t off = (size_t)row * K;
-        const float u32 = (float)p.u[row]; // the float64 original is re-read by the rare float64 fix-up only
+        const float u32 = (float)p.u[row];
+        if (tid == 0) { // (visible after barrier (1); the last readers are in front of the previous row's barrier (8))
+            const double ud = p.u[row];
+            sh.u64 = ud;
+            sh.ulo = (float)(ud - (double)u32);
+        }
 
         float4 lw[4];
         float tmax = -INFINITY;
@@ -333,7 +387,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 m += __shfl_xor_sync(kFull, m, o);
             }
             float v;
-            if (m == 1) { // a single maximum (the usual case): s / 1 = s and log(1) = +0 are exact no-ops
+            if (AESMC_X_ABLATE & 4) {
+                v = __fadd_rn(__fmul_rn(s, 0.01f), vmax);
+            } else if (m == 1) { // a single maximum (the usual case): s / 1 = s and log(1) = +0 are exact no-ops
                 v = __fadd_rn(fd_log1pf(s), vmax);
             } else {
                 const float mf = (float)m;
@@ -424,86 +480,147 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 eb = 0;
             }
         }
-        // segments: maximal runs of pure blocks of one binade INSIDE a warp; a mixed block is its own segment
-        int prev0, prev1, segidx;
-        bool head;
+        // Level 1 (inside the warp): parity maps of consecutive non-mixed blocks compose (on the BIT PATTERN of the chain
+        // value: for s = m 2^(e-23) in binade e, bits(s) + c[bits & 1] are the bits of (m + c) 2^(e-23) while m + c < 2^24
+        // and exactly those of 2^(e+1) when m + c = 2^24, so runs may continue across a binade boundary that is hit
+        // exactly); a mixed block cuts the run.  g = map of the run from its start through this block.
+        const bool mixed = (eb == 0);
+        const unsigned mixmask = __ballot_sync(kFull, mixed);
+        const int kmix = __popc(mixmask & lt_mask); // mixed blocks of this warp before this one
+        int g0 = c0, g1 = c1;                       // (0, 0) unless pure
         {
-            const int eb_prev = __shfl_up_sync(kFull, eb, 1), eb_next = __shfl_down_sync(kFull, eb, 1);
-            head = (lane == 0) || (eb == 0) || (eb_prev != eb);
-            const bool tail = (lane == 31) || (eb_next == 0) || (eb_next != eb);
-            int g0 = c0, g1 = c1, hf = head;
+            const int dist = lane - (31 - __clz((mixmask | 1u) & ((2u << lane) - 1u))); // blocks since the run's first
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int q0 = __shfl_up_sync(kFull, g0, o), q1 = __shfl_up_sync(kFull, g1, o);
-                const int qf = __shfl_up_sync(kFull, hf, o);
-                if (lane >= o && !hf) {
-                    compose(q0, q1, g0, g1, g0, g1);
-                    hf = qf;
-                }
+                if (o <= dist) compose(q0, q1, g0, g1, g0, g1);
             }
-            prev0 = __shfl_up_sync(kFull, g0, 1); // inclusive map of the run up to the previous block
-            prev1 = __shfl_up_sync(kFull, g1, 1);
-            const unsigned endmask = __ballot_sync(kFull, tail);
-            segidx = __popc(endmask & lt_mask);
-            // record: (first padded chunk of the block -- read for mixed blocks only -- | last-of-this-warp flag in
-            // bit 30, binade base bits (pure run) or 0 (mixed block) or -1 (absorbed: identity), c0, c1 (0 unless pure)
-            if (tail) seg_rec[32 * warp + segidx] = make_int4(bl | (lane == 31 ? (1 << 30) : 0), eb > 0 ? (eb << 23) : eb,
-                                                              eb > 0 ? g0 : 0, eb > 0 ? g1 : 0);
         }
-        __syncthreads(); // (5) segment lists
-        if (tid == 32 * (AESMC_X_WALKER_WARP)) {
-            // One thread walks the segments.  This is the serial part of the row (every other warp waits for it),
-            // so the loop carries as little as possible: a pure run is applied to the BIT PATTERN of the chain
-            // value -- for s = m 2^(e-23) in binade e, bits(s) + c[bits & 1] are the bits of (m + c) 2^(e-23) while
-            // m + c < 2^24, and exactly those of 2^(e+1) when m + c = 2^24 (the mantissa field carries into the
-            // exponent) -- i.e. three dependent integer instructions; the binade checks hang off the chain.
-            // The verification is not done here: every block re-checks, in parallel, that its entry value and its
-            // partial sums stayed inside the assumed binade (replay below), which covers every step taken here.
-            int sb = 0; // bits of the chain value (0.0f at the start of a row)
-            const unsigned rec0 = (unsigned)__cvta_generic_to_shared(seg_rec);
-            const unsigned st0 = (unsigned)__cvta_generic_to_shared(seg_state);
-            const unsigned w0 = (unsigned)__cvta_generic_to_shared(bufW4);
-            int idx = 0;
-            int4 rec = lds_v4(rec0);
-#pragma unroll 2
-            for (;;) {
-                const int x = rec.x, base = rec.y;
-                const int sel = (sb & 1) ? rec.w : rec.z;
-                const int nidx = (x >> 30) ? (idx | 31) + 1 : idx + 1; // lists are per warp, 32 slots apart
-                rec = lds_v4(rec0 + 16 * nidx); // next record (one past the end is a harmless read): overlaps with the chain
-                sts_b32(st0 + 4 * idx, sb);
-                sb += sel; // pure run: the whole step; mixed / absorbed records carry c0 = c1 = 0
-                if (base == 0) { // mixed block: its 16 real additions
-                    const unsigned blk = w0 + 16 * (x & 0xffff);
-                    float s = __int_as_float(sb);
+        int prev0 = __shfl_up_sync(kFull, g0, 1), prev1 = __shfl_up_sync(kFull, g1, 1); // map of the run before this block
+        if (lane == 0) prev0 = prev1 = 0;
+        // records for level 2, in particle order: one per mixed block (the map of the run in front of it, then the
+        // block itself) and one for the run that ends the warp's span
+        if (mixed) seg_rec[32 * warp + kmix] = make_int2(prev0, (bl + 1) | ((prev1 - prev0 + 1) << 16));
+        if (lane == 31) {
+            const int nmix = __popc(mixmask);
+            if (!mixed) seg_rec[32 * warp + nmix] = make_int2(g0, (g1 - g0 + 1) << 16);
+            sh.nrec[warp] = nmix + (mixed ? 0 : 1);
+        }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float4 v = lds_f4(blk + 16 * c);
-                        s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
-                    }
-                    sb = __float_as_int(s);
+        for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // run marks of P4 (the previous row's readers are past barrier (1))
+        __syncthreads(); // (5) records
+        if ((AESMC_X_ABLATE & 2) ? (tid == 0) : (warp == NW - 1)) {
+            if (AESMC_X_ABLATE & 2) { sh.total = 1.0f; sh.fail = 0; } else {
+            // Level 2, one warp, lane = record: the maps between two mixed blocks compose by a segmented shuffle scan;
+            // only the mixed blocks themselves (16 real additions each) are walked one after the other.  Verification
+            // is not done here: every block re-checks, in parallel, that its entry value and its partial sums stayed
+            // inside the assumed binade (replay below), which covers every step taken here.
+            // lane -> record.  Usual case: no warp has more than four records, lane = 4 * (warp mod 8) + record, eight
+            // warps per pass (empty slots are identity records); otherwise the lists are compacted by a prefix sum.
+            const int n_l = sh.nrec[lane & (NW - 1)];
+            const bool slots = __all_sync(kFull, n_l <= 4);
+            int pre = n_l;
+            if (!slots) {
+#pragma unroll
+                for (int o = 1; o < NW; o <<= 1) {
+                    const int t = __shfl_up_sync(kFull, pre, o);
+                    if (lane >= o) pre += t;
                 }
-                if (nidx >= 32 * NW) break;
-                idx = nidx;
             }
-            sh.total = __int_as_float(sb);
-            sh.fail = 0;
+            const int R = slots ? 4 * NW : __shfl_sync(kFull, pre, NW - 1);
+            const int start = pre - n_l; // (compacted lists) first record of warp `lane` in particle order
+            int carry = 0;               // bits of the chain value (0.0f at the start of a row)
+            if (lane == 0) seg_state[0] = 0.f;
+            for (int base = 0; base < R; base += 32) {
+                int wi, r, n_wi;
+                bool valid;
+                if (slots) {
+                    wi = (base >> 2) + (lane >> 2);
+                    r = lane & 3;
+                    n_wi = sh.nrec[wi & (NW - 1)];
+                    valid = wi < NW && r < n_wi;
+                } else {
+                    const int gi = base + lane;
+                    const bool starts_here = lane < NW && start >= base && start < base + 32;
+                    const unsigned startmask = __reduce_or_sync(kFull, starts_here ? (1u << (start - base)) : 0u);
+                    const int nbefore = __popc(__ballot_sync(kFull, lane < NW && start < base));
+                    wi = __popc(startmask & ((2u << lane) - 1u)) + nbefore - 1; // the warp record gi belongs to
+                    n_wi = __shfl_sync(kFull, n_l, wi);
+                    r = gi - __shfl_sync(kFull, start, wi);
+                    valid = gi < R;
+                }
+                const int2 rec = valid ? seg_rec[32 * wi + r] : make_int2(0, 1 << 16);
+                const int rblk = (rec.y & 0xffff) - 1; // first padded chunk of the record's mixed block, -1: none
+                const bool opq = rblk >= 0;
+                const unsigned opqmask = __ballot_sync(kFull, opq);
+                // a record starts a new run iff the one before it ends with a mixed block
+                const int dist = lane - (31 - __clz(((opqmask << 1) | 1u) & ((2u << lane) - 1u)));
+                int C0 = rec.x, C1 = rec.x + (rec.y >> 16) - 1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int q0 = __shfl_up_sync(kFull, C0, o), q1 = __shfl_up_sync(kFull, C1, o);
+                    if (o <= dist) compose(q0, q1, C0, C1, C0, C1);
+                }
+                const int carry_in = carry;
+                int s_own = 0;
+                for (unsigned m = (AESMC_X_ABLATE & 1) ? 0u : opqmask; m; m &= m - 1) { // the serial part of the row: ~10 mixed blocks
+                    // (fetching the next block while this one's additions run was measured: the extra registers spill,
+                    // and local-memory round trips on this lone warp cost more than the shuffle + load they hide)
+                    const int pl = __ffs(m) - 1;
+                    const int m0 = __shfl_sync(kFull, C0, pl), m1 = __shfl_sync(kFull, C1, pl);
+                    const int blk = __shfl_sync(kFull, rblk, pl);
+                    const float4 v0 = bufW4[blk], v1 = bufW4[blk + 1], v2 = bufW4[blk + 2], v3 = bufW4[blk + 3];
+                    float s = __int_as_float(carry + ((carry & 1) ? m1 : m0));
+                    s = __fadd_rn(s, v0.x); s = __fadd_rn(s, v0.y); s = __fadd_rn(s, v0.z); s = __fadd_rn(s, v0.w);
+                    s = __fadd_rn(s, v1.x); s = __fadd_rn(s, v1.y); s = __fadd_rn(s, v1.z); s = __fadd_rn(s, v1.w);
+                    s = __fadd_rn(s, v2.x); s = __fadd_rn(s, v2.y); s = __fadd_rn(s, v2.z); s = __fadd_rn(s, v2.w);
+                    s = __fadd_rn(s, v3.x); s = __fadd_rn(s, v3.y); s = __fadd_rn(s, v3.z); s = __fadd_rn(s, v3.w);
+                    carry = __float_as_int(s);
+                    if (lane == pl) s_own = carry;
+                }
+                // chain value after every record: its own for a mixed block, else the run's map applied to the value
+                // after the last mixed block in front of it
+                const unsigned before = opqmask & lt_mask;
+                int sg = __shfl_sync(kFull, s_own, (31 - __clz(before)) & 31);
+                if (!before) sg = carry_in;
+                const int after = opq ? s_own : sg + ((sg & 1) ? C1 : C0);
+                if (valid) {
+                    const int slot = (r == n_wi - 1) ? 32 * (wi + 1) : 32 * wi + r + 1;
+                    if (slot < 32 * NW) seg_state[slot] = __int_as_float(after);
+                }
+                carry = __shfl_sync(kFull, after, 31);
+            }
+            if (lane == 0) {
+                sh.total = __int_as_float(carry);
+                sh.fail = 0;
+            }
+            }
+            cta_barrier(); // (6) exact chain value at every run start
+            // the walker's own weights were dead while it walked (their registers held the mixed blocks): reload them.
+            // Safe after the barrier: the other warps stage latents into chunks below 128 (NW - 1) of the weight buffer,
+            // this warp's padded slice starts at 144 (NW - 1), and its own staging is issued below.
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = bufW4[bl + i];
+                w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        } else {
+            cta_barrier(); // (6), the same barrier from the other warps' side
         }
-        __syncthreads(); // (6) exact chain value at every segment start
         if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
         }
+        float s_in; // exact chain value entering this thread's block = the CDF entry of the particle before it
         {   // every thread replays its own block from its exact entry state
             int badv = 0;
-            const float s0 = seg_state[32 * warp + segidx];
+            int sb = __float_as_int(seg_state[32 * warp + kmix]);
+            sb += (sb & 1) ? prev1 : prev0;
+            s_in = __int_as_float(sb);
             if (eb > 0) {
-                const int sb = __float_as_int(s0);
                 int m = (sb & 0x7fffff) | 0x800000;
-                if ((sb >> 23) != eb) badv = 1;
-                if (!head) m += (m & 1) ? prev1 : prev0;
-                if (m >= 0x1000000) { badv = 1; m = 0x800000; }
+                if ((sb >> 23) != eb) { badv = 1; }
                 float mf = __int_as_float(0x4B000000 | (m & 0x7fffff));
                 const int unscale = (150 - eb) << 23;
 #pragma unroll
@@ -513,23 +630,28 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 }
                 if (mf > 16777216.0f) badv = 1;
             } else {
-                float s = s0;
+                float s = s_in;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { s = __fadd_rn(s, w[j]); w[j] = s; }
             }
-            if (badv) sh.fail = 1; // read after barrier (7)
+            if (AESMC_X_FORCE_FAIL) badv = 1;
+            if (badv && !(AESMC_X_ABLATE & 16)) sh.fail = 1; // read after barrier (8)
         }
         float total = sh.total;
 
-        // ---- P4: closed-form offspring boundaries (inference.py:251,260-264), run marks, max-scan ---
-        int cj[16];
-        int cprev;
+        // ---- P4: closed-form offspring boundaries (inference.py:251,260-264) and run marks ---------------------
+        // particle j owns the positions [c_{j-1}, c_j); the boundary of the particle in front of this thread's block
+        // is recomputed from s_in (the same inputs, hence the same number, as its owner gets)
         for (int attempt = 0;; ++attempt) {
             float rcp = rcp_approx(total);
             rcp = __fmaf_rn(__fmaf_rn(-total, rcp, 1.0f), rcp, rcp);
+            const bool tot_safe = total > 9.3132257e-10f && total < 2.0f;
             // the CDF is non-decreasing: its first entry bounds the others from below, so one test per thread
             // decides whether the hoisted-reciprocal division is the IEEE quotient for all 16
-            const bool safe = total > 9.3132257e-10f && total < 2.0f && w[0] >= 7.8886090522101181e-31f;
+            const bool safe = tot_safe && w[0] >= 7.8886090522101181e-31f;
+            int cp = 0;
+            if (tid != 0 && !AESMC_X_ABLATE) cp = count_positions_below_filtered_x(div_hoisted(s_in, total, rcp, tot_safe), &sh.u64, &sh.ulo, u32, K, Kf, p.tol32);
+            const unsigned marks_s = (unsigned)__cvta_generic_to_shared(bufM);
             const f32x2 rcp2 = splat2(rcp), ntot2 = splat2(-total), K2 = splat2(Kf), nu2 = splat2(-u32);
             const f32x2 magic = splat2(12582912.0f);
 #pragma unroll
@@ -540,7 +662,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     const f32x2 q0 = mul2(c2, rcp2);
                     n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
                 } else {
-                    n2 = pack2(__fdiv_rn(w[j], total), __fdiv_rn(w[j + 1], total));
+                    n2 = pack2(fdiv_rn_call(w[j], total), fdiv_rn_call(w[j + 1], total));
                 }
                 const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
                 const f32x2 tm = add2(tf, magic);
@@ -548,23 +670,24 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 float d0, d1, m0, m1;
                 unpack2(d2, d0, d1);
                 unpack2(tm, m0, m1);
-                cj[j] = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
-                cj[j + 1] = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
-                if (!(fminf(fabsf(d0), fabsf(d1)) > p.tol32)) { // ~0.1 %: the reference's float64 expression
+                int ca = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
+                int cb = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
+                if (!(AESMC_X_ABLATE & 8) && !(fminf(fabsf(d0), fabsf(d1)) > p.tol32)) { // ~0.1 %: the reference's float64 expression
                     float n0, n1;
                     unpack2(n2, n0, n1);
-                    const double u = p.u[row];
-                    if (!(fabsf(d0) > p.tol32)) cj[j] = count_positions_below_slow(n0, u, K);
-                    if (!(fabsf(d1) > p.tol32)) cj[j + 1] = count_positions_below_slow(n1, u, K);
+                    if (!(fabsf(d0) > p.tol32)) ca = count_positions_near_x(n0, u32, &sh.ulo, &sh.u64, K, Kf);
+                    if (!(fabsf(d1) > p.tol32)) cb = count_positions_near_x(n1, u32, &sh.ulo, &sh.u64, K, Kf);
                 }
+                if (AESMC_X_ABLATE) { ca = min(max(ca, cp), K); cb = min(max(cb, ca), K); }
+                if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
+                // bufM[pad_elem(c)] through the shared window (a generic pointer makes the compiler rebuild the
+                // shared base for every store): byte offset 4 c + 16 (c >> 5)
+                if (ca > cp) sts_b32(marks_s + 4 * cp + ((cp >> 5) << 4), 16 * tid + j);
+                if (cb > ca) sts_b32(marks_s + 4 * ca + ((ca >> 5) << 4), 16 * tid + j + 1);
+                cp = cb;
             }
-            if (tid == NT - 1) cj[15] = K; // last particle: positions up to 1.0 stay in range (Q5)
-            if (lane == 31) sh.i1[warp] = cj[15];
-            cprev = __shfl_up_sync(kFull, cj[15], 1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // (the segment lists are dead)
             if (HAS_X && !FUSED) cp_async_wait_all();
-            __syncthreads(); // (7) marks zeroed, warp boundaries, staged latents and the scan's verdict visible
+            __syncthreads(); // (8) run starts, staged latents and the scan's verdict visible
             if (attempt == 0 && sh.fail) {
                 // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
                 __syncthreads();
@@ -575,8 +698,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                         float4 v;
                         if (AESMC_X_ALIAS_X) { // the weights are gone: recompute them from the log-weights this CTA stored
                             const float4 l = reinterpret_cast<const float4 *>(p.log_w + off)[c];
-                            v = make_float4(np_expf_nonpos(__fsub_rn(l.x, lse)), np_expf_nonpos(__fsub_rn(l.y, lse)),
-                                            np_expf_nonpos(__fsub_rn(l.z, lse)), np_expf_nonpos(__fsub_rn(l.w, lse)));
+                            const float lz = AESMC_X_REDUNDANT_TAIL ? lse : sh.lse;
+                            v = make_float4(np_expf_nonpos(__fsub_rn(l.x, lz)), np_expf_nonpos(__fsub_rn(l.y, lz)),
+                                            np_expf_nonpos(__fsub_rn(l.z, lz)), np_expf_nonpos(__fsub_rn(l.w, lz)));
                         } else {
                             v = bufW4[pad_chunk(c)];
                         }
@@ -591,22 +715,20 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 }
                 __syncthreads();
                 total = sh.total;
+                s_in = tid ? reinterpret_cast<const float *>(redo)[pad_elem(16 * tid - 1)] : 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 v = redo[bl + i];
                     w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
                 }
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0);
+                __syncthreads();
                 continue;
             }
             break;
         }
-        if (lane == 0) cprev = warp ? sh.i1[warp - 1] : 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int cp = j ? cj[j - 1] : cprev;
-            if (cj[j] > cp) bufM[pad_elem(cp)] = 16 * tid + j; // particle 16 tid + j owns positions [cp, cj)
-        }
-        __syncthreads(); // (8) run starts
         int id[16];
         {
             int run = 0;
@@ -690,7 +812,8 @@ static int launch_x(const XStepParams &p, int64_t B, cudaStream_t stream)
 {
     constexpr int NCH = 4 * NT;
     constexpr size_t smem = (size_t)(NCH + NCH / 8) * 16 * 2 +
-                            ((HAS_X && !XConfig<HAS_X, FUSED>::kAlias) ? (size_t)NCH * 16 : 0);
+                            ((HAS_X && !XConfig<HAS_X, FUSED>::kAlias) ? (size_t)NCH * 16 : 0) +
+                            (size_t)(NT / 32) * 32 * 8; // weights | run marks | [latents] | scan records
     auto kern = smc_step_x_kernel<NT, HAS_X, FUSED>;
     static int per_sm = 0;
     if (per_sm == 0) {
