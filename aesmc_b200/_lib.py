@@ -27,6 +27,8 @@ _PROTOTYPES = {
                               _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "aesmc_smc_step_lg_dev_f32": [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_uint64, _vp, ctypes.c_uint64, _i64,
                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
+    "aesmc_lgv_propose_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, ctypes.c_uint64, ctypes.c_uint64, _i64, _i64,
+                              _vp, _vp, _vp],
     "aesmc_lg_step_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "aesmc_resample_from_weights_f32": [_vp, _vp, _i64, _i64, _vp, _vp, _int, _vp],
     "aesmc_resample_from_cdf_f32": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],

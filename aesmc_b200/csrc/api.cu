@@ -39,6 +39,8 @@ int launch_smc_step_lg(const float *, const float *, const float *, const float 
                        const double *, float *, float *, float *, int32_t *, float *, int32_t *, int, cudaStream_t);
 int launch_lg_step_bwd(const float *, const float *, const float *, const float *, const float *, const float *, const float *,
                        const float *, const int32_t *, int64_t, int64_t, float *, float *, cudaStream_t);
+int launch_lgv_propose(const float *, const float *, const float *, const float *, const float *, int64_t, int64_t, int,
+                       unsigned long long, unsigned long long, int64_t, int64_t, float *, float *, cudaStream_t);
 int launch_logsumexp_f32(const float *, int64_t, int64_t, float *, int32_t *, cudaStream_t);
 int launch_logsumexp_f64(const double *, int64_t, int64_t, double *, int32_t *, cudaStream_t);
 int launch_lognormexp_f32(const float *, int64_t, int64_t, float *, int, cudaStream_t);
@@ -157,6 +159,21 @@ int aesmc_smc_step_lg_dev_f32(const float *x_prev, const float *y, const float *
     REQUIRE(params_dev, "aesmc_smc_step_lg_dev_f32");
     return smc_step_lg_common("aesmc_smc_step_lg_dev_f32", x_prev, y, noise, q_off, nullptr, params_dev, half_log_2pi, seed,
                               seed_dev, stream_offset, B, K, u, x_new, log_w, lse, idx, x_out, flags, mode, stream);
+}
+
+int aesmc_lgv_propose_f32(const float *x_prev, const float *y, const float *noise, const float *q_row,
+                          const float *params_host, int64_t D, int64_t Dy, int bootstrap, uint64_t seed,
+                          uint64_t stream_offset, int64_t B, int64_t K, float *x_new, float *log_w, void *stream)
+{
+    const char *fn = "aesmc_lgv_propose_f32";
+    REQUIRE(y && params_host && x_new && log_w, fn);
+    REQUIRE(D >= 1 && D <= 16 && Dy >= 1 && Dy <= 16, fn);
+    REQUIRE(bootstrap || q_row, fn);
+    REQUIRE(B >= 0 && K >= 1 && B <= kMaxDim && K * D <= kMaxDim, fn);
+    REQUIRE(x_new != x_prev, fn);
+    if (B == 0) return AESMC_OK;
+    return launch_lgv_propose(x_prev, y, noise, q_row, params_host, D, Dy, bootstrap ? 1 : 0, seed, stream_offset, B, K,
+                              x_new, log_w, S(stream));
 }
 
 int aesmc_lg_step_bwd_f32(const float *x, const float *x_prev, const float *y, const float *q_off, const float *params_dev,

@@ -189,11 +189,10 @@ def model_of(initial, transition, emission, proposal):
     """The ScalarLinearGaussianSSM whose bound methods these four callables are (or the LinkedLGSSM view that
     ``link`` tied to exactly these four objects), else None."""
     view = getattr(proposal, "_aesmc_b200_fused", None)
-    if isinstance(view, LinkedLGSSM):
-        return view if view._mods == (initial, transition, emission, proposal) or all(
-            a is b for a, b in zip(view._mods, (initial, transition, emission, proposal))) else None
+    if isinstance(view, (LinkedLGSSM, LinkedDenseLGSSM)):
+        return view if all(a is b for a, b in zip(view._mods, (initial, transition, emission, proposal))) else None
     owner = getattr(proposal, "__self__", None)
-    if not isinstance(owner, ScalarLinearGaussianSSM):
+    if not isinstance(owner, (ScalarLinearGaussianSSM, VectorLinearGaussianSSM)):
         return None
     for fn, name in ((initial, "initial"), (transition, "transition"), (emission, "emission"), (proposal, "proposal")):
         if getattr(fn, "__self__", None) is not owner or getattr(fn, "__name__", None) != name:
@@ -206,6 +205,8 @@ def applicable(model, observations, num_particles, evidence_only=False):
     (get_loss) -- the one request the fused path can differentiate."""
     if model is None or not torch.cuda.is_available():
         return False
+    if isinstance(model, VectorLinearGaussianSSM):
+        return vector_applicable(model, observations, num_particles)
     first = observations[0]
     if isinstance(first, dict) or not torch.is_tensor(first) or first.dim() != 1 or not first.is_cuda:
         return False
@@ -457,3 +458,239 @@ class GraphedFilter:
     def check(self):
         """Host read of the accumulated NaN / degenerate-row flags (raises like inference.infer)."""
         _ops.raise_on_flags(self.flags)
+
+
+# ------------------------------------------------------------------------------------------------------
+# vector latents: D-dimensional linear-Gaussian models with diagonal noise (BASELINE config 3)
+# ------------------------------------------------------------------------------------------------------
+Independent = torch.distributions.Independent
+
+
+class VectorLinearGaussianSSM:
+    """x_0 ~ N(m0, diag s0^2),  x_t = A x_{t-1} + b + N(0, diag sx^2),  y_t = C x_t + d + N(0, diag sy^2), with a
+    bootstrap proposal or q(x_0 | y_0) = N(W0 y_0 + b0, diag sq0^2), q(x_t | x_{t-1}, y_t) = N(Wx x_{t-1} + Wy y_t + bt,
+    diag sqt^2).  Latents are [B, K, D] tensors (event_shape [D]), observations [B, Dy].
+
+    Like the scalar family it is an ordinary user model (``.initial / .transition / .emission / .proposal`` follow the
+    reference's callable conventions and run through the generic path, the oracle port and the reference itself);
+    ``inference.infer`` recognises its bound methods and, when no gradient is needed, evaluates the model with ONE
+    launch per time step (aesmc_lgv_propose_f32) followed by the step kernel, instead of ~40 torch kernels.
+    Scales may be floats or [D] / [Dy] tensors.  1 <= D, Dy <= 16."""
+
+    def __init__(self, initial_loc, initial_scale, A, transition_scale, C, emission_scale, b=None, d=None,
+                 proposal="bootstrap", device=None):
+        dev = device if device is not None else A.device
+        f = lambda v, n: (v.to(dev, torch.float32) if torch.is_tensor(v) else torch.full((n,), float(v), device=dev)).reshape(n)  # noqa: E731
+        self.device = dev
+        self.A = A.to(dev, torch.float32)
+        self.C = C.to(dev, torch.float32)
+        self.D, self.Dy = self.A.shape[0], self.C.shape[0]
+        D, Dy = self.D, self.Dy
+        self.m0, self.s0 = f(initial_loc, D), f(initial_scale, D)
+        self.b = f(0.0 if b is None else b, D)
+        self.d = f(0.0 if d is None else d, Dy)
+        self.sx, self.sy = f(transition_scale, D), f(emission_scale, Dy)
+        if proposal == "bootstrap":
+            self.prop = None
+        else:
+            self.prop = {"W0": proposal["W0"].to(dev, torch.float32), "b0": f(proposal["b0"], D), "s0": f(proposal["s0"], D),
+                         "Wx": proposal["Wx"].to(dev, torch.float32), "Wy": proposal["Wy"].to(dev, torch.float32),
+                         "bt": f(proposal["bt"], D), "st": f(proposal["st"], D)}
+
+    # ---- the reference's callable conventions (eager torch path) ---------------------------------
+    def initial(self):
+        return Independent(Normal(self.m0, self.s0), 1)
+
+    def transition(self, previous_latents=None, time=None, previous_observations=None):
+        return state.set_batch_shape_mode(Independent(Normal(previous_latents[-1] @ self.A.T + self.b, self.sx), 1), _FULL)
+
+    def emission(self, latents=None, time=None, previous_observations=None):
+        return state.set_batch_shape_mode(Independent(Normal(latents[-1] @ self.C.T + self.d, self.sy), 1), _FULL)
+
+    def proposal(self, previous_latents=None, time=None, observations=None):
+        if self.prop is None:
+            return self.initial() if time == 0 else self.transition(previous_latents=previous_latents, time=time)
+        pr = self.prop
+        if time == 0:
+            return state.set_batch_shape_mode(Independent(Normal(observations[0] @ pr["W0"].T + pr["b0"], pr["s0"]), 1), _BATCH)
+        loc = previous_latents[-1] @ pr["Wx"].T + (observations[time] @ pr["Wy"].T + pr["bt"]).unsqueeze(1)
+        return state.set_batch_shape_mode(Independent(Normal(loc, pr["st"]), 1), _FULL)
+
+    def callables(self):
+        return self.initial, self.transition, self.emission, self.proposal
+
+    def tensors(self):
+        base = [self.m0, self.s0, self.A, self.b, self.sx, self.C, self.d, self.sy]
+        return base + (list(self.prop.values()) if self.prop is not None else [])
+
+    def requires_grad(self):
+        return any(t.requires_grad for t in self.tensors())
+
+    # ---- parameters for aesmc_lgv_propose_f32 ---------------------------------------------------------
+    def kernel_params(self):
+        """(params_t0, params_t) float32 numpy blocks on the host: A | b | sx | C | d | sy | Wx | sq."""
+        D = self.D
+        with torch.no_grad():
+            zero = torch.zeros(D, D, device=self.device)
+            tail0 = [zero, self.s0] if self.prop is None else [zero, self.prop["s0"]]
+            tailt = [zero, self.sx] if self.prop is None else [self.prop["Wx"], self.prop["st"]]
+            emis = [self.C, self.d, self.sy]
+            first = torch.cat([t.reshape(-1) for t in [zero, self.m0, self.s0] + emis + tail0])
+            later = torch.cat([t.reshape(-1) for t in [self.A, self.b, self.sx] + emis + tailt])
+            both = torch.stack([first, later]).float().cpu().numpy()
+        return np.ascontiguousarray(both[0]), np.ascontiguousarray(both[1])
+
+    def proposal_row_means(self, obs):
+        """[T, B, D]: the part of the proposal mean that depends on the observation only (None for a bootstrap model)."""
+        if self.prop is None:
+            return None
+        with torch.no_grad():
+            pr = self.prop
+            first = obs[:1] @ pr["W0"].T + pr["b0"]
+            return torch.cat([first, obs[1:] @ pr["Wy"].T + pr["bt"]]).contiguous()
+
+
+class LinkedDenseLGSSM(VectorLinearGaussianSSM):
+    """A VectorLinearGaussianSSM VIEW of four modules shaped like tests/models/lgssm_dense.py (BASELINE config 3's user
+    model): Initial(loc [D], scale), Transition(A, scale), Emission(C, scale), Proposal(lin_0 = Linear(Dy, D),
+    lin_t = Linear(D + Dy, D) on [x_prev, y_t], log_scale_0, log_scale_t).  Parameters are read at every call."""
+
+    def __init__(self, initial, transition, emission, proposal, bootstrap=False):
+        self._mods = (initial, transition, emission, proposal)
+        self._boot = bootstrap
+        self.device = transition.A.device
+        self.D, self.Dy = transition.A.shape[0], emission.C.shape[0]
+
+    def _v(self, v, n):
+        if torch.is_tensor(v):
+            return v.detach().to(self.device, torch.float32).reshape(-1).expand(n) if v.numel() == 1 else v.detach().to(self.device, torch.float32).reshape(n)
+        return torch.full((n,), float(v), device=self.device)
+
+    m0 = property(lambda s: s._v(s._mods[0].loc, s.D))
+    s0 = property(lambda s: s._v(s._mods[0].scale, s.D))
+    A = property(lambda s: s._mods[1].A.detach())
+    b = property(lambda s: torch.zeros(s.D, device=s.device))
+    sx = property(lambda s: s._v(s._mods[1].scale, s.D))
+    C = property(lambda s: s._mods[2].C.detach())
+    d = property(lambda s: torch.zeros(s.Dy, device=s.device))
+    sy = property(lambda s: s._v(s._mods[2].scale, s.Dy))
+
+    @property
+    def prop(self):
+        q, D = self._mods[3], self.D
+        if self._boot:
+            return None
+        Wt = q.lin_t.weight.detach()
+        return {"W0": q.lin_0.weight.detach(), "b0": q.lin_0.bias.detach(), "s0": q.log_scale_0.detach().exp(),
+                "Wx": Wt[:, :D].contiguous(), "Wy": Wt[:, D:].contiguous(), "bt": q.lin_t.bias.detach(),
+                "st": q.log_scale_t.detach().exp()}
+
+    def requires_grad(self):
+        mods = self._mods
+        ts = [mods[1].A, mods[2].C] + ([] if self._boot else list(mods[3].parameters()))
+        return any(torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+def link_dense(initial, transition, emission, proposal):
+    """Opt modules shaped like tests/models/lgssm_dense.py into the fused vector path (see LinkedDenseLGSSM); returns the
+    view.  A proposal object with attributes ``initial`` and ``transition`` equal to the first two arguments (the prior
+    as proposal) is taken as a bootstrap proposal."""
+    import torch.nn as nn
+    boot = getattr(proposal, "initial", None) is initial and getattr(proposal, "transition", None) is transition
+    ok = (torch.is_tensor(getattr(initial, "loc", None)) and hasattr(initial, "scale")
+          and torch.is_tensor(getattr(transition, "A", None)) and transition.A.dim() == 2 and hasattr(transition, "scale")
+          and torch.is_tensor(getattr(emission, "C", None)) and emission.C.dim() == 2 and hasattr(emission, "scale"))
+    if ok and not boot:
+        D, Dy = transition.A.shape[0], emission.C.shape[0]
+        ok = (isinstance(getattr(proposal, "lin_0", None), nn.Linear) and isinstance(getattr(proposal, "lin_t", None), nn.Linear)
+              and tuple(proposal.lin_0.weight.shape) == (D, Dy) and tuple(proposal.lin_t.weight.shape) == (D, D + Dy)
+              and hasattr(proposal, "log_scale_0") and hasattr(proposal, "log_scale_t"))
+    if not ok:
+        raise ValueError("link_dense() needs Initial(loc [D], scale), Transition(A [D,D], scale), Emission(C [Dy,D], scale) and "
+                         "a Proposal with lin_0 = Linear(Dy, D), lin_t = Linear(D + Dy, D), log_scale_0, log_scale_t (or the "
+                         "prior as proposal)")
+    view = LinkedDenseLGSSM(initial, transition, emission, proposal, bootstrap=boot)
+    try:
+        proposal._aesmc_b200_fused = view
+    except AttributeError:
+        raise ValueError("link_dense(): cannot tag the proposal object")
+    return view
+
+
+def vector_applicable(model, observations, num_particles):
+    """Can this call run through aesmc_lgv_propose_f32 + the step kernel?  (Forward only: anything that needs
+    gradients takes the differentiable generic path.)"""
+    if model is None or not torch.cuda.is_available():
+        return False
+    first = observations[0]
+    if isinstance(first, dict) or not torch.is_tensor(first) or first.dim() != 2 or not first.is_cuda:
+        return False
+    if first.dtype != torch.float32 or first.device != model.A.device or first.size(1) != model.Dy:
+        return False
+    if not (1 <= model.D <= 16 and 1 <= model.Dy <= 16 and num_particles >= 1):
+        return False
+    return not (torch.is_grad_enabled() and model.requires_grad())
+
+
+def infer_fused_vector(model, observations, num_particles, return_log_marginal_likelihood=False, return_latents=True,
+                       return_original_latents=False, return_log_weight=True, return_log_weights=False,
+                       return_ancestral_indices=False, uniforms=None, resampling_mode=None, check_finite=True, noise=None):
+    """SMC with a VectorLinearGaussianSSM: per time step one model launch (sampling + three log-densities) and one
+    step launch (lse, ancestors, D-float gather); arguments and result as inference.infer.
+    noise: optional [T, B, K, D] float32 standard normals instead of the in-kernel Philox stream."""
+    from . import inference
+    T, K, D, Dy = len(observations), num_particles, model.D, model.Dy
+    obs = observations if torch.is_tensor(observations) else torch.stack(list(observations))
+    obs = obs.contiguous()
+    B, dev = obs.shape[1], obs.device
+    p0, pt = model.kernel_params()
+    q_rows = model.proposal_row_means(obs)
+    boot = 1 if q_rows is None else 0
+    flags = _ops.new_flags(dev)
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    keep_originals = return_original_latents or return_latents
+    keep_index = return_ancestral_indices or return_latents
+    originals, log_weights, ancestors = [], [], []
+    lses = torch.empty(T, B, dtype=torch.float32, device=dev)
+    u_all = None
+    if T > 1:
+        u_all = _ops.uniforms_table_to_device(np.random.uniform(size=[T - 1, B]) if uniforms is None else uniforms, T - 1, B, dev)
+    scratch = [torch.empty(B, K, D, dtype=torch.float32, device=dev) for _ in range(2)]
+    x_prev = x_new = log_w = None
+    with torch.no_grad():
+        for t in range(T):
+            last = t == T - 1
+            x_new = torch.empty(B, K, D, dtype=torch.float32, device=dev) if (keep_originals or last) else scratch[t & 1]
+            lw_raw = torch.empty(B, K, dtype=torch.float32, device=dev)
+            nz = None if noise is None else noise[t].contiguous()
+            _lib.call("aesmc_lgv_propose_f32", _lib.ptr(x_prev), _lib.ptr(obs[t]), _lib.ptr(nz),
+                      _lib.ptr(None if q_rows is None else q_rows[t]), (p0 if t == 0 else pt).ctypes.data, D, Dy, boot, seed, t,
+                      B, K, _lib.ptr(x_new), _lib.ptr(lw_raw))
+            log_w, lse, idx, x_res = _ops.smc_step(lw_raw, None, None, None if last else u_all[t], None if last else x_new,
+                                                   flags, resampling_mode, resample=not last)
+            lses[t] = lse
+            if keep_originals:
+                originals.append(x_new)
+            if return_log_weights:
+                log_weights.append(log_w)
+            if not last and keep_index:
+                ancestors.append(idx)
+            x_prev = x_res
+    result = dict.fromkeys(("log_marginal_likelihood", "latents", "original_latents", "log_weight", "log_weights",
+                            "ancestral_indices"))
+    if return_log_marginal_likelihood:
+        result["log_marginal_likelihood"] = (lses - math.log(K)).sum(dim=0)  # inference.py:130-132
+    if return_latents:
+        result["latents"] = inference._trace_genealogy(originals, ancestors, dev)
+    if return_original_latents:
+        result["original_latents"] = originals
+    if return_log_weight:
+        result["log_weight"] = log_w
+    if return_log_weights:
+        result["log_weights"] = log_weights
+    if return_ancestral_indices:
+        result["ancestral_indices"] = [_ops.widen_index(i) for i in ancestors]
+    result["last_latent"] = x_new
+    if check_finite:
+        _ops.raise_on_flags(flags)
+    return result

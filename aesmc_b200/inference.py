@@ -124,6 +124,11 @@ def infer(inference_algorithm, observations, initial, transition, emission, prop
         evidence_only = return_log_marginal_likelihood and not (
             return_latents or return_original_latents or return_log_weight or return_log_weights or return_ancestral_indices)
         if model is not None and fused.applicable(model, observations, K, evidence_only):
+            if isinstance(model, fused.VectorLinearGaussianSSM):  # vector latents: model launch + step launch per time step
+                return fused.infer_fused_vector(model, observations, K, return_log_marginal_likelihood, return_latents,
+                                                return_original_latents, return_log_weight, return_log_weights,
+                                                return_ancestral_indices, uniforms=uniforms,
+                                                resampling_mode=resampling_mode, check_finite=check_finite)
             if torch.is_grad_enabled() and model.requires_grad():
                 # training (losses.get_loss): forward and backward on the fused kernels, one launch per time step each
                 result = dict.fromkeys(("log_marginal_likelihood", "latents", "original_latents", "log_weight",

@@ -113,6 +113,24 @@ int aesmc_smc_step_lg_dev_f32(const float *x_prev, const float *y, const float *
                               float *lse, int32_t *idx, float *x_out, int32_t *flags, int mode, void *stream);
 
 /*
+ * Vector latents (BASELINE config 3): proposal sampling and the three log-densities of a D-dimensional linear-
+ * Gaussian state-space model with diagonal noise, for all B*K particles in one launch -- what the user model's
+ * torch callables compute per time step in inference.py:108-126 (proposal -> state.sample -> three state.log_prob
+ * -> (transition + emission) - proposal):
+ *     x_t | x_{t-1} ~ N(A x_{t-1} + b, diag sx^2)    y_t | x_t ~ N(C x_t + d, diag sy^2)
+ *     q(x_t | x_{t-1}, y_t) = N(Wx x_{t-1} + q_row, diag sq^2)       (bootstrap != 0: q is the transition itself)
+ *   x_prev [B,K,D] resampled latents (NULL at t = 0: then b, sx are the initial loc / scale and Wx is ignored)
+ *   y [B,Dy]; noise [B,K,D] injected standard normals or NULL (Philox4x32-10 keyed by seed / stream_offset)
+ *   q_row [B,D]: the part of the proposal mean that depends on the row only (Wy y_t + bias), NULL iff bootstrap
+ *   params_host (HOST memory, row-major): A [D*D] | b [D] | sx [D] | C [Dy*D] | d [Dy] | sy [Dy] | Wx [D*D] | sq [D]
+ *   out: x_new [B,K,D] proposed latents, log_w [B,K] = (log p(x|x_prev) + log p(y|x)) - log q(x|x_prev,y)
+ * 1 <= D, Dy <= 16.  The log-weights then go through aesmc_smc_step_f32 (lp_a = log_w, x_in = x_new).
+ */
+int aesmc_lgv_propose_f32(const float *x_prev, const float *y, const float *noise, const float *q_row,
+                          const float *params_host, int64_t D, int64_t Dy, int bootstrap, uint64_t seed,
+                          uint64_t stream_offset, int64_t B, int64_t K, float *x_new, float *log_w, void *stream);
+
+/*
  * Backward of one fused linear-Gaussian step: replaces torch autograd of losses.get_loss(..., 'aesmc')
  * (losses.py:5-65 -> inference.py:99-134) for that model family -- the logsumexp gradient, the ancestral
  * gather's scatter-add over descendants (state.py:158-183 backward) and the analytic Normal.log_prob /

@@ -52,9 +52,27 @@ def eager3():
 
 g3 = inference.GraphedInfer("smc", ys, init, trans, emis, prop, K, return_log_marginal_likelihood=True, return_latents=False)
 te, tg = timed(eager3, 5), timed(lambda: g3(ys), 10)
+# the same four modules linked into the fused vector path (aesmc_lgv_propose_f32 + step kernel: 2 launches per time step)
+from aesmc_b200 import fused  # noqa: E402
+fused.link_dense(init, trans, emis, prop)
+tf = timed(eager3, 10)
+ys_host = torch.stack(ys).cpu().pin_memory()
+
+
+def fused3_e2e():  # host observations in, log-evidence out
+    with torch.no_grad():
+        obs = ys_host.to(dev, non_blocking=True)
+        r = inference.infer("smc", obs, init, trans, emis, prop, K, return_log_marginal_likelihood=True, return_latents=False)
+        return r["log_marginal_likelihood"].cpu()
+
+
+tfe = timed(fused3_e2e, 10)
+del prop._aesmc_b200_fused
 print(json.dumps({"config": 3, "model": "10-D dense LGSSM, learned Gaussian proposal", "B": B, "K": K, "T": T, "D": dx,
                   "infer_eager_ms": round(te * 1e3, 2), "infer_graph_replay_ms": round(tg * 1e3, 2),
-                  "particle_steps_per_s_eager": B * K * T / te, "particle_steps_per_s_graph": B * K * T / tg}), flush=True)
+                  "infer_fused_ms": round(tf * 1e3, 3), "infer_fused_e2e_host_obs_ms": round(tfe * 1e3, 3),
+                  "particle_steps_per_s_eager": B * K * T / te, "particle_steps_per_s_graph": B * K * T / tg,
+                  "particle_steps_per_s_fused": B * K * T / tf}), flush=True)
 
 # ---- config 4 ------------------------------------------------------------------------------------------
 for B, K, T in [(64, 1024, 20), (512, 1024, 20)]:

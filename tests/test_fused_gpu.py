@@ -263,3 +263,49 @@ def test_fused_backward_equals_generic_autograd(cuda, proposal):
     (-res["log_marginal_likelihood"].mean()).backward()
     for g, t, n in zip(got, leaves, names + ["p0_y", "p0_off", "pt_x", "pt_y", "pt_off"]):
         np.testing.assert_allclose(g.cpu().numpy(), t.grad.cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=n)
+
+
+@pytest.mark.parametrize("proposal", ["bootstrap", AFFINE])
+def test_fused_scalar_matches_cpu_port_on_shared_noise(cuda, proposal):
+    """Direct parity of the fused scalar path with the CPU port of the reference (inference.py:85-134 with torch CPU
+    distributions and numpy resampling): same injected normals and uniforms on both sides."""
+    import torch.distributions.normal as tdn
+    from oracle import reference_port as port
+    T, B, K = 8, 6, 1024
+    obs_np = lgssm.simulate(T, B, seed=4)
+    noise = torch.randn(T, B, K, generator=torch.Generator().manual_seed(1))
+    u = np.random.default_rng(2).random((T - 1, B))
+    kw = dict(return_log_marginal_likelihood=True, return_log_weights=True, return_ancestral_indices=True,
+              return_original_latents=True)
+    cpu_model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device="cpu")
+    it = iter(noise)
+    orig = tdn._standard_normal
+
+    def fake(shape, dtype, device):
+        z = next(it)
+        return z if tuple(shape) == tuple(z.shape) else z.t().contiguous()
+
+    tdn._standard_normal = fake
+    try:
+        with torch.no_grad():
+            ref = port.infer("smc", [torch.from_numpy(o) for o in obs_np], *cpu_model.callables(), K, uniforms=u, **kw)
+    finally:
+        tdn._standard_normal = orig
+    model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device=cuda)
+    with torch.no_grad():
+        got = fused.infer_fused(model, torch.from_numpy(obs_np).to(cuda), K, uniforms=u, noise=noise.to(cuda), **kw)
+    anc_ref = torch.stack(ref["ancestral_indices"]).numpy()
+    anc_got = torch.stack(got["ancestral_indices"]).cpu().numpy()
+    lw_ref = torch.stack(ref["log_weights"]).numpy()
+    lw_got = torch.stack(got["log_weights"]).cpu().numpy()
+    same_rows = (anc_ref == anc_got).all(axis=(0, 2))
+    print("fused scalar vs CPU port (%s): ancestors differing %d of %d, rows with identical genealogy %d of %d, "
+          "log-weight bits differing at t = 0: %d" % ("bootstrap" if proposal == "bootstrap" else "affine",
+                                                     (anc_ref != anc_got).sum(), anc_ref.size, same_rows.sum(), B,
+                                                     (lw_ref[0].view(np.int32) != lw_got[0].view(np.int32)).sum()))
+    rel = np.abs(lw_got[0] - lw_ref[0]) / np.maximum(np.abs(lw_ref[0]), 1.0)
+    assert rel.max() < 1e-5                                   # north-star tolerance for log-weights
+    assert (anc_ref[0] != anc_got[0]).mean() < 2e-3           # first resampling step: same inputs on both sides
+    assert same_rows.sum() >= B - 2
+    dz = np.abs(got["log_marginal_likelihood"].cpu().numpy() - ref["log_marginal_likelihood"].numpy())
+    assert dz[same_rows].max() < 1e-3 and dz.max() < 1.0
