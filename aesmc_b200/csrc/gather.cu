@@ -332,12 +332,18 @@ __global__ void gather_bwd_atomic_kernel(const T *__restrict__ g, const IdxT *__
     }
 }
 
+bool gather_bwd_rows_supported(const void *g, const void *idx, const void *gsrc, int64_t K, int64_t D);
+int launch_gather_bwd_rows_f32(const float *g, const void *idx, int idx_is_i64, int64_t B, int64_t K, float *gsrc, cudaStream_t st);
+
 template <typename T>
 static int launch_gather_bwd_t(const T *g, const void *idx, int idx_is_i64, int64_t B, int64_t K, int64_t D, T *gsrc,
                                int sorted, cudaStream_t st, const char *name)
 {
     const int threads = 256;
     unsigned gy = (unsigned)(B < 65535 ? B : 65535);
+    if (sorted && sizeof(T) == 4 && gather_bwd_rows_supported(g, idx, gsrc, K, D)) // scalar latents: the row kernel
+        return launch_gather_bwd_rows_f32(reinterpret_cast<const float *>(g), idx, idx_is_i64, B, K,
+                                          reinterpret_cast<float *>(gsrc), st);
     if (sorted) {
         const uintptr_t align = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gsrc);
         const int vw = (D % 4 == 0 && sizeof(T) == 4 && (align & 15) == 0) ? 4 : ((D % 2 == 0 && (align & (2 * sizeof(T) - 1)) == 0) ? 2 : 1);

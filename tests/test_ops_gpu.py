@@ -89,6 +89,36 @@ def test_gather_backward(cuda, sorted_rows, D):
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("K", [128, 1024, 4096, 16384])
+@pytest.mark.parametrize("wide", [False, True])
+def test_gather_backward_row_kernel(cuda, K, wide):
+    """Scalar latents, K % 4 == 0, K <= 16384: the parent-centric row kernel (gather_bwd_rows.cu).  Runs of up to 32
+    children are summed in particle order == the reference's CPU scatter_add, bit for bit; longer ones by a warp."""
+    rng = np.random.default_rng(K)
+    B = 9
+    idx = np.sort(rng.integers(0, K, (B, K)), axis=1)
+    idx[0] = 17                                   # one parent takes everything
+    idx[1] = np.arange(K)                         # every parent exactly one child
+    idx[2, : K // 2] = 0                          # long run at the start, childless parents after it
+    idx[3] = np.sort(rng.integers(K - 3, K, K))   # everything at the end of the row
+    idx[4] = np.repeat(np.arange(K // 32), 32)    # runs of exactly 32: the longest a thread sums itself
+    idx[5] = np.sort(np.concatenate([np.repeat(np.arange(0, K, K // 4)[:3], 33), rng.integers(0, K, K - 99)]))  # runs just over
+    g = torch.from_numpy(rng.standard_normal((B, K)).astype(np.float32)).to(cuda)
+    x = torch.zeros(B, K, device=cuda, requires_grad=True)
+    it = torch.from_numpy(idx).to(cuda)
+    _ops.gather(x, it if wide else it.int(), sorted_rows=True).backward(g)
+    ref = oracle.resample_bwd(g.cpu().numpy(), idx)
+    got = x.grad.cpu().numpy()
+    short = np.array([np.bincount(idx[b], minlength=K).max() <= 32 for b in range(B)])
+    assert short.sum() >= 4 and (~short).sum() >= 3
+    assert np.array_equal(got[short], ref[short])
+    np.testing.assert_allclose(got[~short], ref[~short], rtol=1e-5, atol=1e-4 * np.sqrt(K / 1024))
+    # in the long-run rows every parent with a short run is still exact
+    for b in np.nonzero(~short)[0]:
+        counts = np.bincount(idx[b], minlength=K)
+        assert np.array_equal(got[b][counts <= 32], ref[b][counts <= 32])
+
+
 @pytest.mark.parametrize("D", [1, 2, 5])
 def test_gather_backward_long_rows(cuda, D):
     """Sorted backward on long rows: runs that span many threads and CTAs, odd K (no vector alignment)."""
