@@ -58,7 +58,7 @@ def _worker(rank, world, port, B, out):
         per_row = (model(x).squeeze(-1) - y).detach()
         gathered = distributed.gather_rows(per_row, B)
         mean = distributed.global_mean(per_row, B)
-        # the captured training step refuses to run data-parallel (the NCCL all-reduce stays outside graphs)
+        # the captured training step refuses to run data-parallel on gloo (only NCCL collectives can be captured)
         from aesmc_b200 import train
         try:
             train.GraphedTrainStep([x], 4, "aesmc", None, None, None, None, torch.optim.SGD(model.parameters(), lr=0.1))

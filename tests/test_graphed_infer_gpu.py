@@ -116,3 +116,43 @@ def test_graphed_train_step_nonlinear_mlp_proposal(cuda):
         seen = [float(step(batch)) for _ in range(60)]
         assert all(np.isfinite(seen)), seen[:5]
         assert np.mean(seen[-5:]) < np.mean(seen[:5]), (algorithm, np.mean(seen[:5]), np.mean(seen[-5:]))
+
+
+def test_graphed_prior_sampler_and_dataset(cuda):
+    """train.GraphedPriorSampler: statistics.sample_from_prior as one CUDA graph -- fresh draws per replay with the
+    eager sampler's distribution, feeding the captured training step through SyntheticDataset(graphed=True)."""
+    from aesmc_b200 import statistics, train
+    from tests.models import nonlinear
+    torch.manual_seed(0)
+    init = nonlinear.Initial(cuda)
+    true_trans, true_emis = nonlinear.Transition().to(cuda), nonlinear.Emission().to(cuda)
+    T, B = 8, 4096
+    launches = None
+    sampler = train.GraphedPriorSampler(init, true_trans, true_emis, T, B, keep_latents=True)
+    a = [o.clone() for o in sampler()]
+    b = sampler(clone=True)
+    assert len(a) == T and a[0].shape == b[0].shape and a[0].is_cuda
+    assert not torch.equal(a[0], b[0]) and not torch.equal(a[-1], b[-1])          # fresh noise every replay
+    with torch.no_grad():
+        _, eager = statistics.sample_from_prior(init, true_trans, true_emis, T, B)
+    for t in (0, T - 1):                                                          # same distribution as the eager sampler
+        ge, ee = b[t].double().flatten(), eager[t].double().flatten()
+        se = (ge.var() / B + ee.var() / B).sqrt().item()
+        assert abs(ge.mean().item() - ee.mean().item()) < 6 * se, (t, ge.mean().item(), ee.mean().item())
+        assert 0.8 < (ge.std() / ee.std()).item() < 1.25
+    torch.manual_seed(7)
+    s1 = train.GraphedPriorSampler(init, true_trans, true_emis, 3, 16)
+    x1 = s1(clone=True)
+    torch.manual_seed(7)
+    s2 = train.GraphedPriorSampler(init, true_trans, true_emis, 3, 16)
+    assert all(torch.equal(p, q) for p, q in zip(x1, s2(clone=True)))               # torch.manual_seed controls the stream
+    # the dataset / dataloader front end, feeding a captured training step
+    loader = train.get_synthetic_dataloader(init, true_trans, true_emis, num_timesteps=6, batch_size=32, graphed=True)
+    it = iter(loader)
+    batch = next(it)
+    assert len(batch) == 6 and batch[0].shape[0] == 32 and batch[0].is_cuda
+    trans, emis, prop = nonlinear.Transition(scale=2.0).to(cuda), nonlinear.Emission(mult=0.03).to(cuda), nonlinear.Proposal().to(cuda)
+    opt = torch.optim.Adam(train.get_chained_params(trans, emis, prop), lr=5e-3, capturable=True)
+    step = train.GraphedTrainStep(batch, 128, "aesmc", init, trans, emis, prop, opt)
+    seen = [float(step(next(it))) for _ in range(40)]
+    assert all(np.isfinite(seen)) and np.mean(seen[-8:]) < np.mean(seen[:8])

@@ -1,6 +1,6 @@
 """Two ranks over NCCL (needs >= 2 GPUs; skipped otherwise): batch-sharded AESMC training keeps the
-replicas identical (gradient all-reduce in train()), and sharded inference with globally indexed
-uniforms reproduces the single-process log-evidence row for row."""
+replicas identical (gradient all-reduce in train(), and captured inside train.GraphedTrainStep's CUDA graph),
+and sharded inference with globally indexed uniforms reproduces the single-process log-evidence row for row."""
 import os
 import socket
 
@@ -65,7 +65,25 @@ def _worker(rank, world, port, out):
         ref = flat.clone()
         dist.broadcast(ref, src=0)
         in_sync = bool(torch.allclose(flat, ref, rtol=0, atol=0))
-        flags = torch.tensor([int(same), int(in_sync)], device=dev)
+        # 3. the same training step as ONE CUDA graph per rank, gradient all-reduce captured inside it, fed by the
+        #    graph-captured prior sampler (different data per rank): replicas stay identical and the parameters move
+        torch.distributions.Distribution.set_default_validate_args(False)
+        torch.manual_seed(0)
+        trans2, emis2, prop2 = nonlinear.Transition(2.0).to(dev), nonlinear.Emission(0.03).to(dev), nonlinear.Proposal().to(dev)
+        params2 = list(train.get_chained_params(trans2, emis2, prop2))
+        before = torch.cat([p.detach().reshape(-1) for p in params2]).clone()
+        torch.manual_seed(200 + rank)
+        sampler = train.GraphedPriorSampler(init, nonlinear.Transition().to(dev), nonlinear.Emission().to(dev), 6, 8)
+        opt = torch.optim.Adam(params2, lr=1e-2, capturable=True)
+        step = train.GraphedTrainStep(sampler(clone=True), 64, "aesmc", init, trans2, emis2, prop2, opt)
+        losses_seen = [float(step(sampler())) for _ in range(5)]
+        flat2 = torch.cat([p.detach().reshape(-1) for p in params2])
+        ref2 = flat2.clone()
+        dist.broadcast(ref2, src=0)
+        graph_sync = bool(torch.equal(flat2, ref2)) and bool((flat2 - before).abs().max() > 1e-3) and all(np.isfinite(losses_seen))
+        step.release()  # (a live graph with NCCL kernels would block destroy_process_group below)
+        torch.cuda.synchronize()
+        flags = torch.tensor([int(same), int(in_sync), int(graph_sync)], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
             torch.save(flags.cpu(), out)
@@ -78,6 +96,7 @@ def test_two_rank_nccl(tmp_path):
         pytest.skip("needs 2 GPUs")
     out = str(tmp_path / "flags.pt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    same, in_sync = torch.load(out).tolist()
+    same, in_sync, graph_sync = torch.load(out).tolist()
     assert same == 1, "sharded inference differs from the single-process rows"
     assert in_sync == 1, "replicas diverged: gradient all-reduce missing or wrong"
+    assert graph_sync == 1, "graph-captured data-parallel step: replicas diverged or did not train"
