@@ -295,7 +295,7 @@ def run_native(args):
         torch.cuda.empty_cache()
         ctx = {"rank": rank, "world": world, "dev": dev, "mode": mode, "K": K, "T": T, "B": B}
         for name, fn in (("parity", leg_parity), ("strong", leg_strong), ("sweep_c5", leg_sweep_c5),
-                         ("train_c4", leg_train_c4), ("train_lgssm", leg_train_lgssm)):
+                         ("infer_c3", leg_infer_c3), ("train_c4", leg_train_c4), ("train_lgssm", leg_train_lgssm)):
             try:
                 extras[name] = fn(ctx, ring, arena, u, value, ms_per_step)
             except Exception as exc:  # an extra leg must never take the headline line down with it
@@ -561,10 +561,86 @@ def leg_train_c4(ctx, ring, arena, u, value, ms_per_step):
         ok = torch.tensor([int(torch.equal(ref, flat))], device=dev)
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
         in_sync = bool(ok.item())
-    return {"model": "nonlinear SSM + MLP proposal (hidden 32), get_loss('aesmc') forward + backward + all-reduce + Adam, torch-eager",
-            "rows_per_rank": Bl, "rows_total": Bl * world, "K": K, "T": T, "ms_per_optimizer_step": ms,
-            "allreduce_us": ar_us, "allreduce_floats": int(flat.numel()), "replicas_in_sync": in_sync,
-            "value": Bl * world * K * T / (ms * 1e-3), "unit": UNIT, "scaling": "weak"}
+    out = {"model": "nonlinear SSM + MLP proposal (hidden 32), get_loss('aesmc') forward + backward + all-reduce + Adam, torch-eager",
+           "rows_per_rank": Bl, "rows_total": Bl * world, "K": K, "T": T, "ms_per_optimizer_step": ms,
+           "allreduce_us": ar_us, "allreduce_floats": int(flat.numel()), "replicas_in_sync": in_sync,
+           "value": Bl * world * K * T / (ms * 1e-3), "unit": UNIT, "scaling": "weak"}
+    # the same step replayed as ONE CUDA graph per rank: forward, backward, the NCCL all-reduce (captured inside the
+    # graph) and Adam, fed by the graph-captured prior sampler (train.GraphedPriorSampler: data generated on the device)
+    try:
+        torch.manual_seed(2000 + rank)
+        sampler = train.GraphedPriorSampler(init, nonlinear.Transition().to(dev), nonlinear.Emission().to(dev), T, Bl)
+        gopt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+        gstep = train.GraphedTrainStep(sampler(clone=True), K, "aesmc", init, trans, emis, prop, gopt)
+        for _ in range(2):
+            gstep(sampler())
+        gms = _event_time_ms(lambda: gstep(sampler()), reps, world, dev)
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        g_sync = True
+        if world > 1:
+            ref = flat.clone()
+            torch.distributed.broadcast(ref, src=0)
+            ok = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            g_sync = bool(ok.item())
+        gstep.release()
+        sampler.graph.reset()
+        torch.cuda.synchronize(dev)
+        out.update({"graph_replay_ms_per_optimizer_step": gms, "graph_replay_value": Bl * world * K * T / (gms * 1e-3),
+                    "graph_replay_includes": "on-device prior sampling + forward + backward + captured all-reduce + Adam",
+                    "graph_replicas_in_sync": g_sync})
+    except Exception as exc:  # noqa: BLE001
+        out["graph_replay_error"] = "%s: %s" % (type(exc).__name__, exc)
+    return out
+
+
+def leg_infer_c3(ctx, ring, arena, u, value, ms_per_step):
+    """BASELINE config 3: infer('smc') on the 10-D LGSSM with dense transition / emission and a learned Gaussian proposal
+    (tests/models/lgssm_dense.py), B = K = 1024 per rank, T = 20, observations from pinned host memory, log-evidence back
+    to the host: the user's modules as torch-eager callables, and the same modules linked into the fused vector path
+    (aesmc_b200.fused.link_dense: one model launch + one step launch per time step)."""
+    from aesmc_b200 import fused, inference
+    from tests.models import lgssm_dense
+    world, dev, rank = ctx["world"], ctx["dev"], ctx["rank"]
+    dx = dy = 10
+    B, K, T = 1024, 1024, 20
+    torch.distributions.Distribution.set_default_validate_args(False)
+    A, C = lgssm_dense.make_system(dx, dy, seed=3, device=dev)
+    ys = lgssm_dense.simulate(A, C, T, B, 1.0, 0.5, 0.5, seed=4 + rank).pin_memory()
+    init = lgssm_dense.Initial(dx, 1.0, dev)
+    trans, emis = lgssm_dense.Transition(A, 0.5).to(dev), lgssm_dense.Emission(C, 0.5).to(dev)
+    torch.manual_seed(0)
+    prop = lgssm_dense.Proposal(dx, dy).to(dev)
+
+    def one():
+        with torch.no_grad():
+            obs = ys.to(dev, non_blocking=True)
+            r = inference.infer("smc", obs, init, trans, emis, prop, K, return_log_marginal_likelihood=True, return_latents=False)
+            return r["log_marginal_likelihood"].cpu()
+
+    out = {"model": "10-D dense LGSSM, learned Gaussian proposal", "rows_per_rank": B, "rows_total": B * world, "K": K, "T": T,
+           "D": dx, "h2d_bytes_per_step": int(ys.numel() * 4), "d2h_bytes_per_step": B * 4}
+    for label in ("eager", "fused"):
+        if label == "fused":
+            fused.link_dense(init, trans, emis, prop)
+        for _ in range(2):
+            one()
+        reps = 5 if label == "eager" else 20
+        t0 = time.perf_counter()
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one()
+        torch.cuda.synchronize(dev)
+        ms = max_over_ranks((time.perf_counter() - t0) / reps, world, dev) * 1e3
+        out[label + "_ms"] = ms
+        out[label + "_value"] = B * world * K * T / (ms * 1e-3)
+    out["speedup_fused_over_eager"] = out["eager_ms"] / out["fused_ms"]
+    # fused: model kernel 8 D + 4 bytes, step kernel 8 + 8 D + 8 bytes per particle-step (DESIGN.md section 3.6)
+    peak, _ = load_peaks()
+    out["fused_frac_of_measured_hbm"] = round((16.0 * dx + 20.0) * B * K * T / (out["fused_ms"] * 1e-3) / 1e9 / peak, 4)
+    out["unit"] = UNIT
+    return out
 
 
 
