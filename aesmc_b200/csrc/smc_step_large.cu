@@ -17,11 +17,10 @@
 //                       classifies and composes its blocks against an estimate of its entry value while
 //                       its predecessor is still running, then waits for the exact carry, walks its
 //                       ~20 segments, publishes its exit value and only then replays (exact_scan.cuh).
-//   L4 search    closed-form offspring boundaries c_j; run starts scattered as marks  grid (tiles, B)
-//                into the zeroed idx output itself; the particle whose run covers the
-//                position just before a tile boundary is recorded as that tile's entry
-//   L5 expand    max-scan of the tile's marks from its entry ancestor, idx in place,  grid (tiles, B)
-//                ancestral gather
+//   L4 bounds    closed-form offspring boundary at the end of every input tile         grid (tiles/256, B)
+//   L5 resample  per OUTPUT tile: the input tiles that can own its positions (binary   grid (tiles, B)
+//                search in the L4 table), their boundaries recomputed from the CDF table,
+//                run starts in a shared-memory tile, max-scan, ancestors, ancestral gather
 //
 // Workspace (caller-allocated, aesmc_smc_step_workspace_bytes): W [B,K] f32, per-tile max / sum / offset /
 // scale / entry [B, tiles], per-row max / total / lse, the heap of summation-tree node values of each row,
@@ -65,7 +64,7 @@ struct LargeParams {
     double *tbefore; // [B, ntiles + 1]
     double *tscale;  // [B, ntiles]
     int tiled;
-    int *tenter;     // [B, ntiles] ancestor of the position just before each tile (written by the search)
+    int *tenter;     // [B, ntiles] cend: boundary count of the last particle of each input tile (large_bounds_kernel)
     // exact mode
     float *vals;     // [B, heap_size] node values of numpy's pairwise tree, heap-indexed
     int *rowcnt;     // [B] number of particles equal to the row maximum
@@ -534,102 +533,146 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
     if (span == p.nspans - 1 && tid == 0) p.rowtotal[row] = total;
 }
 
-// ---- L4: closed-form boundaries and run marks ---------------------------------------------------------
-// 16 consecutive particles per thread: the boundary of the predecessor is carried in a register
-template <bool EXACT, bool TILED>
-__global__ void __launch_bounds__(kTileThreads) large_search_kernel(const LargeParams p)
-{
-    const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    if (p.rowbad[row]) return;
-    const int K = p.K;
-    constexpr int kPer = kTile / kTileThreads;
-    const int j0 = tile * kTile + kPer * tid;
-    if (j0 >= K) return;
-    const float *Wrow = p.W + (size_t)row * K;
-    int *marks = p.marks + (size_t)row * K;
-    int *tenter = p.tenter + (size_t)row * p.ntiles;
-    const float total = p.rowtotal[row];
-    const float rcp = refined_rcp(total);
-    const bool safe_total = total > 9.3132257e-10f && total < 2.0f;
-    const double u = p.u[row];
-    const float u32 = (float)u, Kf = (float)K;
-    const double Kd = (double)K, band = Kd * 8.8817841970012523e-16;
-    // the float32 pre-filter sends 2 * tol32 of the particles to float64 anyway: past ~1 % nearly every
-    // warp runs both forms, so large rows use the float64 form alone
-    const bool filtered = K <= 65536;
-    const double t_before = TILED ? p.tbefore[(size_t)row * (p.ntiles + 1) + tile] : 0.0;
-    const double t_scale = TILED ? p.tscale[(size_t)row * p.ntiles + tile] : 0.0;
-    float cdf[kPer];
-    if ((K & 3) == 0) { // j0 + kPer <= K or the tail chunks are past the row
-#pragma unroll
-        for (int i = 0; i < kPer / 4; ++i) {
-            const float4 v = (j0 + 4 * i < K) ? __ldg(reinterpret_cast<const float4 *>(Wrow + j0) + i)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            cdf[4 * i] = v.x; cdf[4 * i + 1] = v.y; cdf[4 * i + 2] = v.z; cdf[4 * i + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kPer; ++i) cdf[i] = (j0 + i < K) ? Wrow[j0 + i] : 0.f;
+// ---- L4 + L5: offspring boundaries, ancestors and gather, fused per OUTPUT tile ---------------------------
+// Round 1 ran an input-centric search (scatter of run marks into the zeroed idx output: a memset, a pass of
+// sector read-modify-writes and a read, 16 bytes of HBM traffic per particle for a table of marks) followed by an
+// expansion per output tile.  Here nothing of the sort touches HBM: a tiny kernel tabulates the boundary count at
+// the END of every input tile, cend[t] = c_{4096 (t + 1) - 1} (monotone in t); the CTA of output tile T finds, by
+// binary search in that table, the input tiles whose particles can own positions of [4096 T, 4096 T + 4096),
+// recomputes their boundaries from the CDF table (tiles without a single offspring are skipped from the table
+// alone, 16-particle blocks that miss the output tile after two evaluations), drops the run starts into a
+// shared-memory tile, max-scans it and writes ancestors and gathered latents.  A particle's boundaries are
+// recomputed by every output tile that looks at its input tile (~2 on average): arithmetic for traffic.
+template <bool EXACT, bool TILED> struct Boundary {
+    const LargeParams &p;
+    float total, rcp, u32, Kf;
+    bool safe_total, filtered;
+    double u, Kd, band;
+    int K;
+    __device__ __forceinline__ Boundary(const LargeParams &p_, int row) : p(p_)
+    {
+        K = p.K;
+        total = p.rowtotal[row];
+        rcp = refined_rcp(total);
+        safe_total = total > 9.3132257e-10f && total < 2.0f;
+        u = p.u[row];
+        u32 = (float)u; Kf = (float)K;
+        Kd = (double)K; band = Kd * 8.8817841970012523e-16;
+        // the float32 pre-filter sends 2 * tol32 of the particles to float64 anyway: past ~1 % nearly every
+        // warp runs both forms, so large rows use the float64 form alone
+        filtered = K <= 65536;
     }
-    auto boundary = [&](float c) {
+    // c: a CDF entry (TILED: a tile-local running sum L, turned into the entry by the tile's offset and scale)
+    __device__ __forceinline__ int operator()(float c, double t_before, double t_scale) const
+    {
         if (TILED) c = cdf_from_tile(c, t_before, t_scale);
         const float cdfn = EXACT ? div_hoisted(c, total, rcp, safe_total) : __fmul_rn(c, rcp);
         return filtered ? count_positions_below_filtered(cdfn, u, u32, K, Kf, p.tol32)
                         : count_positions_below(cdfn, u, K, Kd, band);
-    };
-    // predecessor: in this tile, or the last particle of the previous one (whose CDF entry is before_t)
-    int c_prev = 0;
-    if (j0) c_prev = (TILED && tid == 0) ? boundary(0.f) : boundary(Wrow[j0 - 1]);
-    const int last_i = K - 1 - j0; // particle K-1 owns every remaining position; later slots are past the row
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-        int c = boundary(cdf[i]);
-        if (i >= last_i) c = K;
-        if (c > c_prev) {
-            atomicMax(marks + c_prev, j0 + i); // one writer per entry (c is monotone in j)
-            // a position 4096 T - 1 inside [c_prev, c): this particle is the ancestor entering tile T
-            if ((c >> 12) != (c_prev >> 12))
-                for (int t = (c_prev >> 12) + 1; t <= (c >> 12) && t < p.ntiles; ++t) tenter[t] = j0 + i;
-        }
-        c_prev = c;
     }
+};
+
+// cend[row][t]: boundary count of the last particle of input tile t (K for the last tile: particle K-1 owns every
+// remaining position).  One thread per tile.
+template <bool EXACT, bool TILED>
+__global__ void __launch_bounds__(256) large_bounds_kernel(const LargeParams p)
+{
+    const int row = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.ntiles || p.rowbad[row]) return;
+    int c = p.K;
+    if (t + 1 < p.ntiles) {
+        const Boundary<EXACT, TILED> boundary(p, row);
+        const size_t tt = (size_t)row * p.ntiles + t;
+        c = TILED ? boundary(p.tsum[tt], p.tbefore[(size_t)row * (p.ntiles + 1) + t], p.tscale[tt])
+                  : boundary(p.W[(size_t)row * p.K + (size_t)(t + 1) * kTile - 1], 0.0, 0.0);
+    }
+    p.tenter[(size_t)row * p.ntiles + t] = c;
 }
 
-// ---- L5: expansion of the run marks into ancestor indices, gather -------------------------------------
 // Global traffic is chunk-striped (thread t owns 16-byte chunks t + 256 i: fully coalesced, and the
 // gather of a warp stays within a few sectors because ancestors are sorted); the max-scan wants 16
 // consecutive positions per thread; the padded tile buffer converts between the two.
-__global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeParams p)
+#ifndef AESMC_LARGE_RS_CTAS
+#define AESMC_LARGE_RS_CTAS 4
+#endif
+template <bool EXACT, bool TILED>
+__global__ void __launch_bounds__(kTileThreads, AESMC_LARGE_RS_CTAS) large_resample_kernel(const LargeParams p)
 {
-    __shared__ __align__(16) int s_tile[kTile + kTile / 8];
+    extern __shared__ __align__(16) int s_dyn[];
+    int *s_tile = s_dyn;                          // [kTile + kTile / 8] run marks, then ancestors, of the output tile
+    int *s_cend = s_dyn + kTile + kTile / 8;      // [ntiles]
     __shared__ int s_w[32];
     constexpr int kPer = kTile / kTileThreads;
     const int row = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)row * p.K;
-    const int K = p.K, k0 = tile * kTile, n = min(kTile, K - k0);
+    const int K = p.K, p0 = tile * kTile, n = min(kTile, K - p0), p1 = p0 + n, nt = p.ntiles;
     if (p.rowbad[row]) { // identity ancestry keeps downstream gathers in range
-        for (int k = tid; k < n; k += kTileThreads) p.idx[off + k0 + k] = k0 + k;
+        for (int k = tid; k < n; k += kTileThreads) p.idx[off + p0 + k] = p0 + k;
         if (p.x_in) {
-            const size_t xo = (off + k0) * p.D;
+            const size_t xo = (off + p0) * p.D;
             for (int e = tid; e < n * p.D; e += kTileThreads) p.x_out[xo + e] = p.x_in[xo + e];
         }
         return;
     }
-    // ancestor of the position just before the tile: the particle whose run [c_{j-1}, c_j) covers it
-    const int enter = k0 ? p.tenter[(size_t)row * p.ntiles + tile] : 0;
     const bool vec = (K & 3) == 0;
     int4 *s_tile4 = reinterpret_cast<int4 *>(s_tile);
-    if (vec) {
+    for (int t = tid; t < nt; t += kTileThreads) s_cend[t] = p.tenter[(size_t)row * nt + t];
+    for (int c = tid; c < (kTile + kTile / 8) / 4; c += kTileThreads) s_tile4[c] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    // input tiles that can own positions of [p0, p1): first t with cend[t] > p0 ... first t with cend[t] >= p1
+    int t_first, t_last;
+    {
+        int lo = 0, hi = nt - 1; // cend[nt - 1] = K > p0
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cend[mid] > p0) hi = mid; else lo = mid + 1; }
+        t_first = lo;
+        hi = nt - 1;             // cend[nt - 1] = K >= p1
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cend[mid] >= p1) hi = mid; else lo = mid + 1; }
+        t_last = lo;
+    }
+    const Boundary<EXACT, TILED> boundary(p, row);
+    const float *Wrow = p.W + off;
+    for (int t = t_first; t <= t_last; ++t) {
+        const int c_tile_in = t ? s_cend[t - 1] : 0;       // boundary of the particle in front of the tile
+        if (s_cend[t] == c_tile_in) continue;               // not one offspring in the whole tile
+        const double t_before = TILED ? p.tbefore[(size_t)row * (nt + 1) + t] : 0.0;
+        const double t_scale = TILED ? p.tscale[(size_t)row * nt + t] : 0.0;
+        const int j0 = t * kTile + kPer * tid;
+        // the block's 16 CDF entries, loaded before anybody knows whether the block matters: one global round trip
+        // per input tile instead of two (the kernel is latency-bound: ~3 input tiles per output tile, 4 CTAs per SM;
+        // measured: 562 -> 529 us per step at B = 64, K = 10^6.  Letting every thread evaluate the boundary in front
+        // of its block itself -- no exchange, no barrier in this loop -- was slower again: 562 us)
+        float cdf[kPer];
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < kPer / 4; ++i) {
-            const int c = tid + kTileThreads * i;
-            s_tile4[pad_chunk(c)] = (4 * c < n) ? reinterpret_cast<const int4 *>(p.marks + off + k0)[c] : make_int4(0, 0, 0, 0);
+            for (int i = 0; i < kPer / 4; ++i) {
+                const float4 v = (j0 + 4 * i < K) ? __ldg(reinterpret_cast<const float4 *>(Wrow + j0) + i)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                cdf[4 * i] = v.x; cdf[4 * i + 1] = v.y; cdf[4 * i + 2] = v.z; cdf[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) cdf[i] = (j0 + i < K) ? Wrow[j0 + i] : 0.f;
         }
-    } else {
+        // the boundary at the end of this thread's block, and (from its neighbour) of the particle in front of it
+        int c_end = s_cend[t];
+        if (j0 + kPer < (t + 1) * kTile && j0 + kPer < K) c_end = boundary(cdf[kPer - 1], t_before, t_scale);
+        else if (j0 >= K) c_end = K;
+        int c_prev = __shfl_up_sync(kFull, c_end, 1);
+        if (lane == 0) c_prev = tid ? 0 : c_tile_in;
+        __syncthreads(); // warp boundaries travel through shared memory (the previous pass's readers are done)
+        if (lane == 31) s_w[warp] = c_end;
+        __syncthreads();
+        if (lane == 0 && tid) c_prev = s_w[warp - 1];
+        if (j0 < K && c_end > c_prev && c_prev < p1 && c_end > p0) { // the block owns positions of this output tile
+            const int last_i = K - 1 - j0; // particle K-1 owns every remaining position; later slots are past the row
+            int cp = c_prev;
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            const int k = tid + kTileThreads * i;
-            s_tile[pad_elem(k)] = (k < n) ? p.marks[off + k0 + k] : 0;
+            for (int i = 0; i < kPer; ++i) {
+                int c = (i == kPer - 1) ? c_end : boundary(cdf[i], t_before, t_scale);
+                if (i >= last_i) c = K;
+                if (c > cp && cp < p1 && c > p0) s_tile[pad_elem(max(cp, p0) - p0)] = j0 + i; // one writer per position
+                cp = c;
+            }
         }
     }
     __syncthreads();
@@ -649,9 +692,9 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
     }
     int pre = __shfl_up_sync(kFull, incl, 1);
     if (lane == 0) pre = 0;
+    __syncthreads(); // (s_w carried the boundary exchange above)
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    pre = max(pre, enter);
     for (int v = 0; v < warp; ++v) pre = max(pre, s_w[v]);
 #pragma unroll
     for (int i = 0; i < kPer / 4; ++i)
@@ -665,9 +708,9 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
             const int c = tid + kTileThreads * i;
             if (4 * c < n) {
                 const int4 v = s_tile4[pad_chunk(c)];
-                reinterpret_cast<int4 *>(p.idx + off + k0)[c] = v;
+                reinterpret_cast<int4 *>(p.idx + off + p0)[c] = v;
                 if (gather1)
-                    reinterpret_cast<float4 *>(p.x_out + off + k0)[c] = make_float4(__ldg(xin + v.x), __ldg(xin + v.y), __ldg(xin + v.z), __ldg(xin + v.w));
+                    reinterpret_cast<float4 *>(p.x_out + off + p0)[c] = make_float4(__ldg(xin + v.x), __ldg(xin + v.y), __ldg(xin + v.z), __ldg(xin + v.w));
             }
         }
         if (!p.x_in || gather1) return;
@@ -675,11 +718,11 @@ __global__ void __launch_bounds__(kTileThreads) large_expand_kernel(const LargeP
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             const int k = tid + kTileThreads * i;
-            if (k < n) p.idx[off + k0 + k] = s_tile[pad_elem(k)];
+            if (k < n) p.idx[off + p0 + k] = s_tile[pad_elem(k)];
         }
         if (!p.x_in) return;
     }
-    gather_rows(p.x_in + off * p.D, p.x_out + (off + k0) * p.D, s_tile, n, p.gather);
+    gather_rows(p.x_in + off * p.D, p.x_out + (off + p0) * p.D, s_tile, n, p.gather);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -727,7 +770,7 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     p.W = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * K * 4);
-    p.marks = idx; // the run marks live in the idx output until the expansion rewrites each tile in place
+    p.marks = nullptr; // (round 1 kept a table of run marks in the idx output; the fused resampling kernel needs none)
     p.tmax = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
     p.tsum = reinterpret_cast<float *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
     p.tenter = reinterpret_cast<int *>(ws); ws += align_up((size_t)B * p.ntiles * 4);
@@ -753,7 +796,6 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
     p.rowcnt = p.stats + 4;
     cudaError_t e = cudaMemsetAsync(p.rowbad, 0, (size_t)B * 4, stream);
     if (e == cudaSuccess && exact) e = cudaMemsetAsync(p.slots, 0, zero_bytes, stream);
-    if (e == cudaSuccess && idx) e = cudaMemsetAsync(p.marks, 0, (size_t)B * K * 4, stream);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     const dim3 grid((unsigned)p.ntiles, (unsigned)B);
     if (exact) large_prep_kernel<false><<<grid, kTileThreads, 0, stream>>>(p);
@@ -784,11 +826,21 @@ int launch_smc_step_large(const float *a, const float *b, const float *c, const 
         count_launch();
     }
     if (idx) {
-        if (exact) large_search_kernel<true, false><<<grid, kTileThreads, 0, stream>>>(p);
-        else large_search_kernel<false, true><<<grid, kTileThreads, 0, stream>>>(p);
-        count_launch();
-        large_expand_kernel<<<grid, kTileThreads, 0, stream>>>(p);
-        count_launch();
+        const dim3 bgrid((unsigned)((p.ntiles + 255) / 256), (unsigned)B);
+        const size_t smem_rs = (size_t)(kTile + kTile / 8 + p.ntiles) * 4;
+        if (smem_rs > 200 * 1024) { set_error("aesmc_smc_step_ws_f32: K=%lld exceeds the multi-CTA path (tile table)", (long long)K); return AESMC_ERR_UNSUPPORTED; }
+        auto launch_rs = [&](auto bounds, auto resample) {
+            cudaError_t err = cudaFuncSetAttribute(resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rs);
+            if (err != cudaSuccess) return err;
+            bounds<<<bgrid, 256, 0, stream>>>(p);
+            count_launch();
+            resample<<<grid, kTileThreads, smem_rs, stream>>>(p);
+            count_launch();
+            return cudaSuccess;
+        };
+        e = exact ? launch_rs(large_bounds_kernel<true, false>, large_resample_kernel<true, false>)
+                  : launch_rs(large_bounds_kernel<false, true>, large_resample_kernel<false, true>);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return AESMC_ERR_LAUNCH; }
     }
     if (exact && idx && getenv("AESMC_DEBUG_STATS")) { // debugging aid: synchronises
         int h[4] = {0, 0, 0, 0};

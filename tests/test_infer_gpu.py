@@ -117,9 +117,14 @@ def test_loss_and_gradients_match_port(cuda, algorithm):
         got = losses.get_loss([torch.from_numpy(o).to(cuda) for o in obs], K, algorithm, *gpu_models, uniforms=u)
     got.backward()
     np.testing.assert_allclose(got.item(), ref.item(), rtol=1e-5)
+    worst = 0.0
     for mc, mg in zip(cpu_models[1:], gpu_models[1:]):
         for pc, pg in zip(mc.parameters(), mg.parameters()):
-            np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), rtol=2e-3, atol=1e-5)
+            g, r = pg.grad.cpu().numpy(), pc.grad.numpy()
+            worst = max(worst, float(np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-2))))
+            # float32 sums over B K T terms in different orders (GPU row reductions vs torch's CPU kernels): measured 3e-6, bound 5e-5 relative
+            np.testing.assert_allclose(g, r, rtol=5e-5, atol=1e-6)
+    print("%s: max relative gradient difference vs the CPU port %.2e" % (algorithm, worst))
     with pytest.raises(UnboundLocalError):
         losses.get_loss([torch.from_numpy(o).to(cuda) for o in obs], K, "smc", *gpu_models)
 
