@@ -110,8 +110,6 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-// barrier 0 of the CTA, for the one place where the warps reach it on different code paths (warp-uniform branch)
-__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void sts_b32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // IEEE division out of line (rare paths: keeps eight inlined copies of its range handling out of the instruction cache)
@@ -595,17 +593,21 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 sh.fail = 0;
             }
             }
-            cta_barrier(); // (6) exact chain value at every run start
-            // the walker's own weights were dead while it walked (their registers held the mixed blocks): reload them.
+            // this warp's own weights are dead while it walks (their registers hold the mixed blocks; the assignment tells
+            // the compiler so) and are reloaded after the barrier
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = 0.f;
+        }
+        __syncthreads(); // (6) exact chain value at every run start
+        if (warp == NW - 1) {
             // Safe after the barrier: the other warps stage latents into chunks below 128 (NW - 1) of the weight buffer,
-            // this warp's padded slice starts at 144 (NW - 1), and its own staging is issued below.
+            // this warp's padded slice starts at 144 (NW - 1), and its own staging is issued after the __syncwarp.
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 v = bufW4[bl + i];
                 w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-        } else {
-            cta_barrier(); // (6), the same barrier from the other warps' side
+            __syncwarp();
         }
         if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;

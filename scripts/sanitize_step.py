@@ -29,6 +29,56 @@ for mode in ("exact", "fast"):
         r = fused.infer_fused(model, obs, 512, return_log_marginal_likelihood=True, resampling_mode=mode)
     torch.cuda.synchronize()
     assert torch.isfinite(r["log_marginal_likelihood"]).all()
+# round 2: the second-generation exact row kernel at every CTA size (with / without latents), its fused-model instance
+# with the training backward (aesmc_lg_step_bwd_f32), the vector model kernel, the per-output-tile resampling of the
+# multi-CTA path on collapsed weights, the parent-centric gather backward and the multi-warp row statistics
+for K in (1024, 2048, 4096, 8192, 16384):
+    for spread in (1.0, 12.0):
+        B = 3
+        a, b, c = [spread * torch.randn(B, K, device=dev, generator=gen) for _ in range(3)]
+        xs = torch.randn(B, K, device=dev, generator=gen)
+        u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
+        flags = _ops.new_flags(dev)
+        o1 = _ops.smc_step(a, b, c, u, xs, flags, "exact", True)
+        o2 = _ops.smc_step(a, None, None, u, None, flags, "exact", True)
+        torch.cuda.synchronize()
+        assert int(flags.item()) == 0 and int(o1[2].max()) < K and int(o2[2].max()) < K
+from tests.models import lgssm  # noqa: E402
+from aesmc_b200 import losses  # noqa: E402
+init, trans, emis, prop = lgssm.Initial(0.0, 1.0), lgssm.Transition(0.5, 1.0).to(dev), lgssm.Emission(0.5, 0.5).to(dev), lgssm.Proposal(0.9, 0.9).to(dev)
+fused.link(init, trans, emis, prop)
+obs = [torch.randn(3, device=dev, generator=gen) for _ in range(4)]
+for K in (1024, 600):
+    loss = losses.get_loss(obs, K, "aesmc", init, trans, emis, prop)
+    loss.backward()
+torch.cuda.synchronize()
+A, C = torch.randn(10, 10, device=dev, generator=gen) * 0.2, torch.randn(7, 10, device=dev, generator=gen) * 0.3
+vm = fused.VectorLinearGaussianSSM(torch.zeros(10), 1.0, A, 0.5, C, 0.7, device=dev)
+with torch.no_grad():
+    rv = fused.infer_fused_vector(vm, torch.randn(3, 2, 7, device=dev, generator=gen), 1000, return_log_marginal_likelihood=True)
+assert torch.isfinite(rv["log_marginal_likelihood"]).all()
+for B, K in [(2, 70000), (1, 300000)]:
+    a = 20.0 * torch.randn(B, K, device=dev, generator=gen)          # collapsed: whole input tiles without offspring
+    xs = torch.randn(B, K, device=dev, generator=gen)
+    u = torch.rand(B, dtype=torch.float64, device=dev, generator=gen)
+    flags = _ops.new_flags(dev)
+    for mode in ("exact", "fast"):
+        o = _ops.smc_step(a, None, None, u, xs, flags, mode, True)
+        torch.cuda.synchronize()
+        assert int(o[2].max()) < K and bool((o[2][:, 1:] >= o[2][:, :-1]).all())
+for K in (1024, 4096):
+    B = 3
+    xg = torch.randn(B, K, device=dev, generator=gen).requires_grad_()
+    ix = torch.sort(torch.randint(0, K, (B, K), device=dev, generator=gen), dim=1).values
+    ix[0, 10:900] = ix[0, 10]
+    ix[1] = ix[1, 5]
+    for t in (ix.int(), ix):
+        _ops.gather(xg, t, True).sum().backward()
+big = torch.randn(160, 4096, device=dev, generator=gen)
+_ops.logsumexp_rows(big); _ops.log_ess_rows(big); _ops.weighted_moments(torch.randn(160, 4096, device=dev, generator=gen), big)
+big = torch.randn(600, 1024, device=dev, generator=gen)
+_ops.logsumexp_rows(big); _ops.log_ess_rows(big); _ops.weighted_moments(torch.randn(600, 1024, device=dev, generator=gen), big)
+torch.cuda.synchronize()
 from aesmc_b200 import statistics  # noqa: E402
 for D in (1, 2, 4, 10):
     B, K = 3, 1001 if D == 1 else 1000
