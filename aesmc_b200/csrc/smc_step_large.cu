@@ -562,14 +562,48 @@ template <bool EXACT, bool TILED> struct Boundary {
         // warp runs both forms, so large rows use the float64 form alone
         filtered = K <= 65536;
     }
-    // c: a CDF entry (TILED: a tile-local running sum L, turned into the entry by the tile's offset and scale)
-    __device__ __forceinline__ int operator()(float c, double t_before, double t_scale) const
+    // c: a CDF entry (exact mode: the reference's float64 comparison, common.cuh)
+    __device__ __forceinline__ int operator()(float c, double, double) const
     {
-        if (TILED) c = cdf_from_tile(c, t_before, t_scale);
-        const float cdfn = EXACT ? div_hoisted(c, total, rcp, safe_total) : __fmul_rn(c, rcp);
+        const float cdfn = div_hoisted(c, total, rcp, safe_total);
         return filtered ? count_positions_below_filtered(cdfn, u, u32, K, Kf, p.tol32)
                         : count_positions_below(cdfn, u, K, Kd, band);
     }
+    // FAST mode owes nobody the reference's float64 rounding of (u + k) / K: #{k >= 0 : u + k < cdfn K} = ceil(cdfn K - u)
+    // evaluated EXACTLY in 32.32 fixed point -- cdfn = m 2^e is a float32, so m K is an exact 45-bit integer; u is
+    // taken to 2^-32 -- a dozen integer instructions instead of the float64 sequence (which rows beyond 65 536
+    // particles would run for every particle), monotone in cdfn by construction.
+    unsigned long long u_fix;
+    __device__ __forceinline__ void init_fast() { u_fix = (unsigned long long)(u * 4294967296.0); }
+    __device__ __forceinline__ int from_cdf_fast(float cdf) const
+    {
+        const float cdfn = fminf(__fmul_rn(cdf, rcp), 1.0f);
+        const int b = __float_as_int(cdfn);
+        int ex = b >> 23; // cdfn >= 0
+        const unsigned m = ex ? ((b & 0x7fffff) | 0x800000) : (b & 0x7fffff);
+        ex = max(ex, 1);
+        const unsigned long long P = (unsigned long long)m * (unsigned)K; // cdfn K = P 2^(ex - 150)
+        const int sh = ex - 150 + 32;                                     // <= 9 because cdfn <= 1
+        const unsigned long long T = sh >= 0 ? (P << sh) : (sh > -64 ? (P >> (-sh)) : 0ull);
+        const long long n = (long long)(T - u_fix);
+        const int c = n <= 0 ? 0 : (int)((unsigned long long)(n + 0xffffffffll) >> 32);
+        return min(c, K);
+    }
+};
+// FAST: the CDF entry of a particle from its tile-local running sum L, in float32 with one rounding, clamped to the
+// next tile's offset -- which IS, by definition, the entry of the tile's last particle: monotone inside a tile (fma
+// is monotone in L) and across tiles (the clamp), consistent between the table of tile ends and the particles
+struct TileCdf {
+    float b0, b1, sc;
+    __device__ __forceinline__ TileCdf(const LargeParams &p, int row, int t, bool on = true)
+    {
+        b0 = b1 = sc = 0.f;
+        if (!on) return;
+        const double *before = p.tbefore + (size_t)row * (p.ntiles + 1) + t;
+        b0 = __double2float_rn(before[0]); b1 = __double2float_rn(before[1]);
+        sc = __double2float_rn(p.tscale[(size_t)row * p.ntiles + t]);
+    }
+    __device__ __forceinline__ float operator()(float L) const { return fminf(__fmaf_rn(L, sc, b0), b1); }
 };
 
 // cend[row][t]: boundary count of the last particle of input tile t (K for the last tile: particle K-1 owns every
@@ -581,10 +615,13 @@ __global__ void __launch_bounds__(256) large_bounds_kernel(const LargeParams p)
     if (t >= p.ntiles || p.rowbad[row]) return;
     int c = p.K;
     if (t + 1 < p.ntiles) {
-        const Boundary<EXACT, TILED> boundary(p, row);
-        const size_t tt = (size_t)row * p.ntiles + t;
-        c = TILED ? boundary(p.tsum[tt], p.tbefore[(size_t)row * (p.ntiles + 1) + t], p.tscale[tt])
-                  : boundary(p.W[(size_t)row * p.K + (size_t)(t + 1) * kTile - 1], 0.0, 0.0);
+        Boundary<EXACT, TILED> boundary(p, row);
+        if (TILED) {
+            boundary.init_fast();
+            c = boundary.from_cdf_fast(TileCdf(p, row, t).b1);
+        } else {
+            c = boundary(p.W[(size_t)row * p.K + (size_t)(t + 1) * kTile - 1], 0.0, 0.0);
+        }
     }
     p.tenter[(size_t)row * p.ntiles + t] = c;
 }
@@ -629,13 +666,15 @@ __global__ void __launch_bounds__(kTileThreads, AESMC_LARGE_RS_CTAS) large_resam
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cend[mid] >= p1) hi = mid; else lo = mid + 1; }
         t_last = lo;
     }
-    const Boundary<EXACT, TILED> boundary(p, row);
+    Boundary<EXACT, TILED> bnd(p, row);
+    if (TILED) bnd.init_fast();
     const float *Wrow = p.W + off;
     for (int t = t_first; t <= t_last; ++t) {
         const int c_tile_in = t ? s_cend[t - 1] : 0;       // boundary of the particle in front of the tile
         if (s_cend[t] == c_tile_in) continue;               // not one offspring in the whole tile
-        const double t_before = TILED ? p.tbefore[(size_t)row * (nt + 1) + t] : 0.0;
-        const double t_scale = TILED ? p.tscale[(size_t)row * nt + t] : 0.0;
+        const TileCdf tcdf(p, row, t, TILED);
+        auto boundary = [&](float v, double, double) { return TILED ? bnd.from_cdf_fast(tcdf(v)) : bnd(v, 0.0, 0.0); };
+        const double t_before = 0.0, t_scale = 0.0;
         const int j0 = t * kTile + kPer * tid;
         // the block's 16 CDF entries, loaded before anybody knows whether the block matters: one global round trip
         // per input tile instead of two (the kernel is latency-bound: ~3 input tiles per output tile, 4 CTAs per SM;
