@@ -47,6 +47,26 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// ---- one-dimensional bulk copy global -> shared, completion on an mbarrier (TMA engine, no tensor map) ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic accesses to the buffer before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+                 ::"r"(b), "r"(phase) : "memory");
+}
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
     float4 v;
@@ -181,6 +201,9 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 #ifndef AESMC_X_REDUNDANT_TAIL
 #define AESMC_X_REDUNDANT_TAIL 0 // 1: every warp evaluates the scalar lse tail itself, no barrier (3) (measured: -1 %)
 #endif
+#ifndef AESMC_X_BULK
+#define AESMC_X_BULK 1 // 1: the latent row is staged by ONE bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA
+#endif                 // engine moves the 4 K bytes, no thread issues a load) instead of four 16-byte cp.async per thread
 #ifndef AESMC_X_FORCE_FAIL
 #define AESMC_X_FORCE_FAIL 0 // 1 (test builds): every row fails the scan's verification and takes the sequential redo path
 #endif
@@ -230,7 +253,13 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     const unsigned lt_mask = (1u << lane) - 1u;
     const float Kf = (float)K;
 
-    if (tid == 0) sh.bad = 0;
+    constexpr bool kBulkX = AESMC_X_BULK && HAS_X && !FUSED && AESMC_X_ALIAS_X;
+    __shared__ __align__(8) unsigned long long xbar; // completion of the latent row's bulk copy
+    unsigned xphase = 0;
+    if (tid == 0) {
+        sh.bad = 0;
+        if (kBulkX) mbar_init(&xbar, 1);
+    }
     __syncthreads();
 
     for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
@@ -608,8 +637,11 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
             __syncwarp();
+            // the weight buffer is free: one bulk copy stages this row's latents into it for the gather in P5 (issued
+            // here, by the warp whose reload above was the buffer's last reader)
+            if (kBulkX && lane == 0) bulk_copy_g2s(bufX4, p.x_in + off, (unsigned)K * 4u, &xbar);
         }
-        if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
+        if (HAS_X && !FUSED && AESMC_X_ALIAS_X && !kBulkX) { // the weight buffer is free: stage this row's latents into it for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
@@ -688,7 +720,11 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 if (cb > ca) sts_b32(marks_s + 4 * ca + ((ca >> 5) << 4), 16 * tid + j + 1);
                 cp = cb;
             }
-            if (HAS_X && !FUSED) cp_async_wait_all();
+            if (kBulkX) {
+                if (attempt == 0) { mbar_wait(&xbar, xphase); xphase ^= 1u; }
+            } else if (HAS_X && !FUSED) {
+                cp_async_wait_all();
+            }
             __syncthreads(); // (8) run starts, staged latents and the scan's verdict visible
             if (attempt == 0 && sh.fail) {
                 // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
