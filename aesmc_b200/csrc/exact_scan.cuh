@@ -52,8 +52,9 @@ struct LocalCarry {
     float s_in;
     __device__ __forceinline__ float anchor() const { return s_in; }
     __device__ __forceinline__ float slack() const { return 0.f; }
-    __device__ __forceinline__ float wait() const { return s_in; }
+    __device__ __forceinline__ float wait(int) const { return s_in; }
     __device__ __forceinline__ void publish(float) const {}
+    __device__ __forceinline__ void publish_map(int, int, int) const {}
 };
 
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
@@ -185,8 +186,18 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
     // ---- one thread walks the segments: O(1) per pure run, 16 float additions per mixed block -----
     // (lane 0 of the LAST warp: the warp scheduler favours the highest warp id among eligible warps, and
     // every other warp is about to wait at the barrier for this chain)
-    if (tid == NT - 32) {
-        float s = carry.wait();
+    if (tid >= NT - 32) {
+      // chained spans: a span that is ONE pure (or absorbed) segment publishes its map before waiting for its carry,
+      // and the whole warp looks back over the spans in front of it (decoupled look-back, smc_step_large.cu)
+      if constexpr (Carry::kChained) {
+          if (lane == 0 && sh.nseg == 1) {
+              const int4 only = seg_rec[0];
+              // (an all-absorbed span is the identity only above a threshold its consumer could not check: it waits)
+              if (only.y > 0) carry.publish_map(only.y, only.z, only.w);
+          }
+      }
+      float s = carry.wait(lane);
+      if (lane == 0) {
         int fail = 0;
         int nseg = sh.nseg;
         if constexpr (Carry::kChained) {
@@ -217,6 +228,7 @@ __device__ __forceinline__ bool exact_cumsum_blocked(float (&w)[kScanItems], flo
         if (!fail) carry.publish(s);
         sh.total = s;
         sh.fail = fail;
+      }
     }
     __syncthreads();
 

@@ -389,25 +389,65 @@ __global__ void __launch_bounds__(1024) large_fold_kernel(const LargeParams p)
 // chains overlap and 512-thread spans (two CTAs per SM, one hiding the other's barriers) have the better
 // throughput.  Measured on B200, K = 1e6: B = 8: 71 vs 106 us; B = 64: 331 vs 256 us.
 
+// Decoupled look-back (round 2).  A slot holds, in its top two bits, 0: nothing yet, 1: a MAP, 2: the span's exit
+// VALUE (float bits).  A span whose blocks all lie in one binade e -- most spans of a long row: half of them sit in
+// [0.5, 1) -- is, as a whole, the parity map bits -> bits + c[bits & 1]; it publishes (e, c0, c1 - c0) as soon as the
+// map is composed, BEFORE its own carry has arrived, and its exit value later.  A waiting span reads the 32 slots in
+// front of it in one round trip (one per lane), takes the nearest value and pushes it through the maps in between;
+// every map is validated on the way (entry in binade e, no carry out of it beyond an exact hit of 2^(e+1)) -- a map
+// composed against a missed estimate simply does not apply, and the waiter falls back to its predecessor's value.
+// The serial chain of a row is thereby cut from one segment walk per span to one per span that crosses a binade.
 struct ChainedCarry {
     static constexpr bool kChained = true;
     float est, tol;
-    const unsigned long long *prev; // slot of the previous span, nullptr for the first
-    unsigned long long *mine;
+    int span;                 // index of this span in its row (0: the chain starts at 0.0)
+    unsigned long long *mine; // slots of a row are contiguous: mine[-1 - d] is the span d + 1 in front
     __device__ __forceinline__ float anchor() const { return est; }
     __device__ __forceinline__ float slack() const { return tol; }
-    __device__ __forceinline__ float wait() const
+    static __device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p)
     {
-        if (prev == nullptr) return 0.f;
         unsigned long long v;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(prev) : "memory");
-        } while ((v >> 32) == 0ull);
-        return __int_as_float((int)(unsigned)v);
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+    // called by every lane of one warp; the result is returned to all of them
+    __device__ __forceinline__ float wait(int lane) const
+    {
+        if (span == 0) return 0.f;
+        for (;;) {
+            // lane d looks at the span d + 1 in front; in front of span 0 the chain value is 0.0
+            const unsigned long long v = (lane < span) ? ld_slot(mine - 1 - lane) : (2ull << 62);
+            const unsigned st = (unsigned)(v >> 62);
+            const unsigned valmask = __ballot_sync(kFull, st == 2u), mapmask = __ballot_sync(kFull, st == 1u);
+            if (!valmask) continue; // 32 maps in a row (or nothing yet): poll again
+            const int dv = __ffs(valmask) - 1;
+            const unsigned nearer = (1u << dv) - 1u;
+            if ((mapmask & nearer) != nearer) continue; // a nearer span has published nothing yet
+            int sb = __shfl_sync(kFull, (int)(unsigned)v, dv);
+            bool ok = true;
+            for (int k = dv - 1; k >= 0; --k) { // forward through the maps (warp-uniform)
+                const unsigned long long m = __shfl_sync(kFull, v, k);
+                const int e = (int)((m >> 27) & 0xffu), c0 = (int)(m & 0x1ffffffu), c1 = c0 + (int)((m >> 25) & 3u) - 1;
+                const int mm = (sb & 0x7fffff) | 0x800000;
+                const int c = (mm & 1) ? c1 : c0;
+                if ((sb >> 23) != e || mm + c > 0x1000000) { ok = false; break; }
+                sb += c; // (m + c = 2^24 carries into the exponent: exactly 2^(e+1))
+            }
+            if (ok) return __int_as_float(sb);
+            unsigned long long pv; // a map did not apply: wait for the predecessor's own value
+            do { pv = ld_slot(mine - 1); } while ((pv >> 62) != 2ull);
+            return __int_as_float((int)(unsigned)pv);
+        }
+    }
+    __device__ __forceinline__ void publish_map(int e, int c0, int c1) const
+    {
+        const unsigned long long v = (1ull << 62) | ((unsigned long long)(unsigned)(e & 0xff) << 27) |
+                                     ((unsigned long long)(unsigned)(c1 - c0 + 1) << 25) | (unsigned long long)(unsigned)(c0 & 0x1ffffff);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mine), "l"(v) : "memory");
     }
     __device__ __forceinline__ void publish(float s) const
     {
-        const unsigned long long v = (1ull << 32) | (unsigned long long)(unsigned)__float_as_int(s);
+        const unsigned long long v = (2ull << 62) | (unsigned long long)(unsigned)__float_as_int(s);
         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mine), "l"(v) : "memory");
     }
 };
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) large_exact_scan_kernel(const L
     ChainedCarry cc;
     cc.est = (float)part;
     cc.tol = cc.est * 5.9604644775390625e-08f * (8.0f * sqrtf((float)base) + 64.0f);
-    cc.prev = span ? slots + span - 1 : nullptr;
+    cc.span = span;
     cc.mine = slots + span;
     float w[kScanItems];
     auto load_block = [&]() {
