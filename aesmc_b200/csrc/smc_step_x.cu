@@ -31,6 +31,7 @@
 // Everything it cannot take (other K, vector latents, fast mode, the fused-model step, no resampling)
 // stays with smc_step_reg.cu / smc_step.cu / smc_step_large.cu.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "pairwise.cuh"
 #include "lg_model.cuh"
@@ -78,6 +79,8 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p)
 // np_expf_nonpos_pair (common.cuh) with the denominator evaluated NEGATED: fma(-c1, r, -c0) and
 // fma(., r, -1) are the exact negations of the reference's Horner steps (rounding is symmetric), which
 // saves the two sign flips per pair; rcp.approx of the negated value is the negated reciprocal.
+// NORMAL: the caller guarantees x >= -86.5, i.e. exponents >= -125 and normal results: no subnormal handling, no branch
+template <bool NORMAL>
 __device__ __forceinline__ void np_expf_nonpos_pair_x(float x0, float x1, float &r0, float &r1)
 {
     const f32x2 x = pack2(x0, x1);
@@ -103,7 +106,7 @@ __device__ __forceinline__ void np_expf_nonpos_pair_x(float x0, float x1, float 
     unpack2(poly, p0, p1);
     unpack2(tq, t0, t1);
     const int k0 = __float_as_int(t0) - 0x4B400000, k1 = __float_as_int(t1) - 0x4B400000;
-    if (min(k0, k1) >= -125) {
+    if (NORMAL || min(k0, k1) >= -125) {
         r0 = __int_as_float(__float_as_int(p0) + (k0 << 23));
         r1 = __int_as_float(__float_as_int(p1) + (k1 << 23));
         return;
@@ -131,6 +134,15 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
     return v;
 }
 __device__ __forceinline__ void sts_b32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// run mark of a particle that owns the positions [cp, c): marks[pad_elem(cp)] = id iff c > cp, as ONE predicated store
+// (an if around a store costs BSSY + BRA + BSYNC per particle; the alu pipe, which takes one warp-instruction every two
+// cycles per scheduler, is what bounds this kernel); byte offset of pad_elem(cp): 4 cp + 16 (cp >> 5)
+__device__ __forceinline__ void mark_run(unsigned marks_s, int cp, int c, int id)
+{
+    const unsigned addr = marks_s + 4 * cp + ((cp >> 5) << 4);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %1, %2;\n\t@p st.shared.b32 [%0], %3;\n\t}"
+                 ::"r"(addr), "r"(c), "r"(cp), "r"(id) : "memory");
+}
 
 // IEEE division out of line (rare paths: keeps eight inlined copies of its range handling out of the instruction cache)
 static __device__ __noinline__ float fdiv_rn_call(float a, float b) { return __fdiv_rn(a, b); }
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         }
 
         float4 lw[4];
-        float tmax = -INFINITY;
+        float tmax = -INFINITY, tmin = INFINITY; // (tmin: do all of this thread's weights stay normal numbers?)
         int bad = 0;
         if (FUSED) {
             // propose x ~ q(. | x_prev, y), then log_w = (log p(x | x_prev) + log p(y | x)) - log q(x | x_prev, y), each
@@ -314,6 +326,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 bufX4[gc + 32 * i] = xv; // the gather source of P5 (the previous row's readers passed the barrier below)
                 bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
                 tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                tmin = fminf(fminf(tmin, fminf(v.x, v.y)), fminf(v.z, v.w));
                 lw[i] = v;
             }
         } else {
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 __stcs(o4 + 32 * i, v);
                 bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
                 tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                tmin = fminf(fminf(tmin, fminf(v.x, v.y)), fminf(v.z, v.w));
                 lw[i] = v;
             }
         }
@@ -375,21 +389,25 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         {
             const bool has_max = (tmax == vmax); // this thread holds (one of) the row maxima: excluded and counted
             int cnt = 0;
+            auto pass = [&](auto normal) { // one branch per thread and pass instead of one per pair (see np_expf_nonpos_pair_x)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = lw[i];
-                const float dx = __fsub_rn(v.x, vmax), dy = __fsub_rn(v.y, vmax), dz = __fsub_rn(v.z, vmax), dw = __fsub_rn(v.w, vmax);
-                float4 e;
-                np_expf_nonpos_pair_x(dx, dy, e.x, e.y);
-                np_expf_nonpos_pair_x(dz, dw, e.z, e.w);
-                if (has_max) {
-                    if (dx == 0.0f) { e.x = 0.0f; ++cnt; }
-                    if (dy == 0.0f) { e.y = 0.0f; ++cnt; }
-                    if (dz == 0.0f) { e.z = 0.0f; ++cnt; }
-                    if (dw == 0.0f) { e.w = 0.0f; ++cnt; }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = lw[i];
+                    const float dx = __fsub_rn(v.x, vmax), dy = __fsub_rn(v.y, vmax), dz = __fsub_rn(v.z, vmax), dw = __fsub_rn(v.w, vmax);
+                    float4 e;
+                    np_expf_nonpos_pair_x<decltype(normal)::value>(dx, dy, e.x, e.y);
+                    np_expf_nonpos_pair_x<decltype(normal)::value>(dz, dw, e.z, e.w);
+                    if (has_max) {
+                        if (dx == 0.0f) { e.x = 0.0f; ++cnt; }
+                        if (dy == 0.0f) { e.y = 0.0f; ++cnt; }
+                        if (dz == 0.0f) { e.z = 0.0f; ++cnt; }
+                        if (dw == 0.0f) { e.w = 0.0f; ++cnt; }
+                    }
+                    bufW4[sl + 36 * i] = e;
                 }
-                bufW4[sl + 36 * i] = e;
-            }
+            };
+            // (warp-uniform choice: a divergent warp would run both forms)
+            if (__all_sync(kFull, __fsub_rn(tmin, vmax) >= -86.5f)) pass(std::true_type{}); else pass(std::false_type{});
             __syncwarp();
             // leaf L = particles [128 L, 128 L + 128) of the warp's span, summed by lanes 8L .. 8L+7 with numpy's
             // 8 strided accumulators; xor-shuffles 1, 2, 4 combine them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
@@ -437,14 +455,17 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         // ---- P2b: normalised weights np.exp(lw - lse) (math.py:49), striped -> blocked inside the warp --
         float w[16];
         {
+            auto pass = [&](auto normal) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = lw[i];
-                float4 e;
-                np_expf_nonpos_pair_x(__fsub_rn(v.x, lse), __fsub_rn(v.y, lse), e.x, e.y);
-                np_expf_nonpos_pair_x(__fsub_rn(v.z, lse), __fsub_rn(v.w, lse), e.z, e.w);
-                bufW4[sl + 36 * i] = e;
-            }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = lw[i];
+                    float4 e;
+                    np_expf_nonpos_pair_x<decltype(normal)::value>(__fsub_rn(v.x, lse), __fsub_rn(v.y, lse), e.x, e.y);
+                    np_expf_nonpos_pair_x<decltype(normal)::value>(__fsub_rn(v.z, lse), __fsub_rn(v.w, lse), e.z, e.w);
+                    bufW4[sl + 36 * i] = e;
+                }
+            };
+            if (__all_sync(kFull, __fsub_rn(tmin, lse) >= -86.5f)) pass(std::true_type{}); else pass(std::false_type{});
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -685,7 +706,8 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             const bool safe = tot_safe && w[0] >= 7.8886090522101181e-31f;
             int cp = 0;
             if (tid != 0 && !AESMC_X_ABLATE) cp = count_positions_below_filtered_x(div_hoisted(s_in, total, rcp, tot_safe), &sh.u64, &sh.ulo, u32, K, Kf, p.tol32);
-            const unsigned marks_s = (unsigned)__cvta_generic_to_shared(bufM);
+            unsigned marks_s = (unsigned)__cvta_generic_to_shared(bufM);
+            asm volatile("" : "+r"(marks_s)); // one register for the whole loop: do not rebuild the shared base per store
             const f32x2 rcp2 = splat2(rcp), ntot2 = splat2(-total), K2 = splat2(Kf), nu2 = splat2(-u32);
             const f32x2 magic = splat2(12582912.0f);
 #pragma unroll
@@ -716,8 +738,8 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
                 // bufM[pad_elem(c)] through the shared window (a generic pointer makes the compiler rebuild the
                 // shared base for every store): byte offset 4 c + 16 (c >> 5)
-                if (ca > cp) sts_b32(marks_s + 4 * cp + ((cp >> 5) << 4), 16 * tid + j);
-                if (cb > ca) sts_b32(marks_s + 4 * ca + ((ca >> 5) << 4), 16 * tid + j + 1);
+                mark_run(marks_s, cp, ca, 16 * tid + j);
+                mark_run(marks_s, ca, cb, 16 * tid + j + 1);
                 cp = cb;
             }
             if (kBulkX) {
