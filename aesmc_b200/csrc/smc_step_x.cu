@@ -710,38 +710,43 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             asm volatile("" : "+r"(marks_s)); // one register for the whole loop: do not rebuild the shared base per store
             const f32x2 rcp2 = splat2(rcp), ntot2 = splat2(-total), K2 = splat2(Kf), nu2 = splat2(-u32);
             const f32x2 magic = splat2(12582912.0f);
+            const float tol32 = p.tol32;
+            int idb = 16 * tid;
+            asm volatile("" : "+r"(idb)); // (kept in a register: otherwise the thread index is re-read for every pair)
+            // one warp-uniform choice of the division form for all eight pairs instead of a branch inside every pair
+            auto pairs = [&](auto safe_c) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                f32x2 n2;
-                if (safe) {
-                    const f32x2 c2 = pack2(w[j], w[j + 1]);
-                    const f32x2 q0 = mul2(c2, rcp2);
-                    n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
-                } else {
-                    n2 = pack2(fdiv_rn_call(w[j], total), fdiv_rn_call(w[j + 1], total));
+                for (int j = 0; j < 16; j += 2) {
+                    f32x2 n2;
+                    if (decltype(safe_c)::value) {
+                        const f32x2 c2 = pack2(w[j], w[j + 1]);
+                        const f32x2 q0 = mul2(c2, rcp2);
+                        n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
+                    } else {
+                        n2 = pack2(fdiv_rn_call(w[j], total), fdiv_rn_call(w[j + 1], total));
+                    }
+                    const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
+                    const f32x2 tm = add2(tf, magic);
+                    const f32x2 d2 = sub2(tf, sub2(tm, magic)); // tf - rint(tf), exact
+                    float d0, d1, m0, m1;
+                    unpack2(d2, d0, d1);
+                    unpack2(tm, m0, m1);
+                    int ca = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
+                    int cb = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
+                    if (!(AESMC_X_ABLATE & 8) && !(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
+                        float n0, n1;
+                        unpack2(n2, n0, n1);
+                        if (!(fabsf(d0) > tol32)) ca = count_positions_near_x(n0, u32, &sh.ulo, &sh.u64, K, Kf);
+                        if (!(fabsf(d1) > tol32)) cb = count_positions_near_x(n1, u32, &sh.ulo, &sh.u64, K, Kf);
+                    }
+                    if (AESMC_X_ABLATE) { ca = min(max(ca, cp), K); cb = min(max(cb, ca), K); }
+                    if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
+                    mark_run(marks_s, cp, ca, idb + j);
+                    mark_run(marks_s, ca, cb, idb + j + 1);
+                    cp = cb;
                 }
-                const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
-                const f32x2 tm = add2(tf, magic);
-                const f32x2 d2 = sub2(tf, sub2(tm, magic)); // tf - rint(tf), exact
-                float d0, d1, m0, m1;
-                unpack2(d2, d0, d1);
-                unpack2(tm, m0, m1);
-                int ca = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
-                int cb = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
-                if (!(AESMC_X_ABLATE & 8) && !(fminf(fabsf(d0), fabsf(d1)) > p.tol32)) { // ~0.1 %: the reference's float64 expression
-                    float n0, n1;
-                    unpack2(n2, n0, n1);
-                    if (!(fabsf(d0) > p.tol32)) ca = count_positions_near_x(n0, u32, &sh.ulo, &sh.u64, K, Kf);
-                    if (!(fabsf(d1) > p.tol32)) cb = count_positions_near_x(n1, u32, &sh.ulo, &sh.u64, K, Kf);
-                }
-                if (AESMC_X_ABLATE) { ca = min(max(ca, cp), K); cb = min(max(cb, ca), K); }
-                if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
-                // bufM[pad_elem(c)] through the shared window (a generic pointer makes the compiler rebuild the
-                // shared base for every store): byte offset 4 c + 16 (c >> 5)
-                mark_run(marks_s, cp, ca, 16 * tid + j);
-                mark_run(marks_s, ca, cb, 16 * tid + j + 1);
-                cp = cb;
-            }
+            };
+            if (__all_sync(kFull, safe)) pairs(std::true_type{}); else pairs(std::false_type{});
             if (kBulkX) {
                 if (attempt == 0) { mbar_wait(&xbar, xphase); xphase ^= 1u; }
             } else if (HAS_X && !FUSED) {
