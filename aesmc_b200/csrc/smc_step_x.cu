@@ -176,7 +176,7 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
     const float tf = __fmaf_rn(cdf_entry, Kf, -u32);
     const float tm = __fadd_rn(tf, 12582912.0f);
     const float d = __fsub_rn(tf, __fsub_rn(tm, 12582912.0f)); // tf - rint(tf), exact
-    if (fabsf(d) > tol32) return __float_as_int(tm) - 0x4B400000 + (d > 0.0f); // ceil(tf) <= K
+    if (fabsf(d) > tol32) return __float_as_int(__fadd_ru(tf, 12582912.0f)) - 0x4B400000; // ceil(tf) <= K
     return count_positions_near_x(cdf_entry, u32, u_lo_sh, u_sh, K, Kf);
 }
 
@@ -728,11 +728,14 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
                     const f32x2 tm = add2(tf, magic);
                     const f32x2 d2 = sub2(tf, sub2(tm, magic)); // tf - rint(tf), exact
+                    // ceil(tf): 1.5 * 2^23 + tf rounded TOWARDS +INF is exactly 1.5 * 2^23 + ceil(tf) (ulp 1 in that binade)
+                    f32x2 tmu;
+                    asm("add.rp.f32x2 %0, %1, %2;" : "=l"(tmu) : "l"(tf), "l"(magic));
                     float d0, d1, m0, m1;
                     unpack2(d2, d0, d1);
-                    unpack2(tm, m0, m1);
-                    int ca = __float_as_int(m0) - 0x4B400000 + (d0 > 0.0f); // ceil(tf)
-                    int cb = __float_as_int(m1) - 0x4B400000 + (d1 > 0.0f);
+                    unpack2(tmu, m0, m1);
+                    int ca = __float_as_int(m0) - 0x4B400000;
+                    int cb = __float_as_int(m1) - 0x4B400000;
                     if (!(AESMC_X_ABLATE & 8) && !(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
                         float n0, n1;
                         unpack2(n2, n0, n1);
