@@ -188,6 +188,9 @@ __device__ __forceinline__ void compose(int p0, int p1, int n0, int n1, int &h0,
 }
 
 template <int NW> struct Shared {
+    int cur_row, next_row;    // the row being processed / the next one (kept here, not in a register that is live --
+                              // and spilled -- across the whole row); written after barrier (1), read after barrier (2)
+    unsigned xphase;          // phase parity of the latent row's bulk-copy barrier
     double u64;               // this row's uniform (read by the rarest fix-up of the boundary count)
     float ulo;                // u64 - fl32(u64) (read by the rare float32 fix-up)
     float wmax[NW], part[NW], wsum[NW];
@@ -267,15 +270,17 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
 
     constexpr bool kBulkX = AESMC_X_BULK && HAS_X && !FUSED && AESMC_X_ALIAS_X;
     __shared__ __align__(8) unsigned long long xbar; // completion of the latent row's bulk copy
-    unsigned xphase = 0;
     if (tid == 0) {
         sh.bad = 0;
+        sh.xphase = 0;
         if (kBulkX) mbar_init(&xbar, 1);
     }
     __syncthreads();
 
-    for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
-        const size_t off = (size_t)row * K;
+    auto cur_off = [&]() { return (size_t)(*(volatile int *)&sh.cur_row) * K; }; // (from barrier (2) on)
+    int row = blockIdx.x;
+    while (row < p.B) {
+        const size_t off = (size_t)row * K; // P1 only: later phases use cur_off()
         const float u32 = (float)p.u[row];
         if (tid == 0) { // (visible after barrier (1); the last readers are in front of the previous row's barrier (8))
             const double ud = p.u[row];
@@ -334,20 +339,24 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             const float4 *__restrict__ b4 = p.b ? reinterpret_cast<const float4 *>(p.b + off) + gc : nullptr;
             const float4 *__restrict__ c4 = p.c ? reinterpret_cast<const float4 *>(p.c + off) + gc : nullptr;
             float4 *__restrict__ o4 = reinterpret_cast<float4 *>(p.log_w + off) + gc;
+            auto combine = [&](auto both) { // (a + b) - c; the three-operand case without per-load predicates
+                constexpr bool kBoth = decltype(both)::value;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 v = ld_stream(a4 + 32 * i);
-                f32x2 lo = pack2(v.x, v.y), hi = pack2(v.z, v.w);
-                if (b4) { const float4 t = ld_stream(b4 + 32 * i); lo = add2(lo, pack2(t.x, t.y)); hi = add2(hi, pack2(t.z, t.w)); }
-                if (c4) { const float4 t = ld_stream(c4 + 32 * i); lo = sub2(lo, pack2(t.x, t.y)); hi = sub2(hi, pack2(t.z, t.w)); }
-                unpack2(lo, v.x, v.y);
-                unpack2(hi, v.z, v.w);
-                __stcs(o4 + 32 * i, v);
-                bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                tmin = fminf(fminf(tmin, fminf(v.x, v.y)), fminf(v.z, v.w));
-                lw[i] = v;
-            }
+                for (int i = 0; i < 4; ++i) {
+                    float4 v = ld_stream(a4 + 32 * i);
+                    f32x2 lo = pack2(v.x, v.y), hi = pack2(v.z, v.w);
+                    if (kBoth || b4) { const float4 t = ld_stream(b4 + 32 * i); lo = add2(lo, pack2(t.x, t.y)); hi = add2(hi, pack2(t.z, t.w)); }
+                    if (kBoth || c4) { const float4 t = ld_stream(c4 + 32 * i); lo = sub2(lo, pack2(t.x, t.y)); hi = sub2(hi, pack2(t.z, t.w)); }
+                    unpack2(lo, v.x, v.y);
+                    unpack2(hi, v.z, v.w);
+                    __stcs(o4 + 32 * i, v);
+                    bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                    tmax = fmaxf(fmaxf(tmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                    tmin = fminf(fminf(tmin, fminf(v.x, v.y)), fminf(v.z, v.w));
+                    lw[i] = v;
+                }
+            };
+            if (b4 && c4) combine(std::true_type{}); else combine(std::false_type{});
         }
         {
             const float wm = warp_max(tmax);
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (bad) sh.bad = 1;
         }
         __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
+        if (tid == 0) { sh.cur_row = row; sh.next_row = row + (int)gridDim.x; }
         if (HAS_X && !FUSED && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
@@ -382,6 +392,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             __syncthreads();
             if (tid == 0) sh.bad = 0;
             __syncthreads();
+            row += gridDim.x;
             continue;
         }
 
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             lse = v;
             if (tid == NT - 32) {
                 if (!AESMC_X_REDUNDANT_TAIL) sh.lse = v;
-                if (p.lse) p.lse[row] = v;
+                if (p.lse) p.lse[*(volatile int *)&sh.cur_row] = v;
             }
         }
         if (!AESMC_X_REDUNDANT_TAIL) {
@@ -660,10 +671,10 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             __syncwarp();
             // the weight buffer is free: one bulk copy stages this row's latents into it for the gather in P5 (issued
             // here, by the warp whose reload above was the buffer's last reader)
-            if (kBulkX && lane == 0) bulk_copy_g2s(bufX4, p.x_in + off, (unsigned)K * 4u, &xbar);
+            if (kBulkX && lane == 0) bulk_copy_g2s(bufX4, p.x_in + cur_off(), (unsigned)K * 4u, &xbar);
         }
         if (HAS_X && !FUSED && AESMC_X_ALIAS_X && !kBulkX) { // the weight buffer is free: stage this row's latents into it for the gather in P5
-            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
+            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + cur_off()) + gc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
         }
@@ -751,11 +762,12 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             };
             if (__all_sync(kFull, safe)) pairs(std::true_type{}); else pairs(std::false_type{});
             if (kBulkX) {
-                if (attempt == 0) { mbar_wait(&xbar, xphase); xphase ^= 1u; }
+                if (attempt == 0) mbar_wait(&xbar, *(volatile unsigned *)&sh.xphase);
             } else if (HAS_X && !FUSED) {
                 cp_async_wait_all();
             }
             __syncthreads(); // (8) run starts, staged latents and the scan's verdict visible
+            if (kBulkX && attempt == 0 && tid == 0) sh.xphase ^= 1u; // (read again in front of the next row's barrier (8))
             if (attempt == 0 && sh.fail) {
                 // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
                 __syncthreads();
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     for (int c = 0; c < NCH; ++c) {
                         float4 v;
                         if (AESMC_X_ALIAS_X) { // the weights are gone: recompute them from the log-weights this CTA stored
-                            const float4 l = reinterpret_cast<const float4 *>(p.log_w + off)[c];
+                            const float4 l = reinterpret_cast<const float4 *>(p.log_w + cur_off())[c];
                             const float lz = AESMC_X_REDUNDANT_TAIL ? lse : sh.lse;
                             v = make_float4(np_expf_nonpos(__fsub_rn(l.x, lz)), np_expf_nonpos(__fsub_rn(l.y, lz)),
                                             np_expf_nonpos(__fsub_rn(l.z, lz)), np_expf_nonpos(__fsub_rn(l.w, lz)));
@@ -833,13 +845,15 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         }
 
         // ---- P5: indices out, fused ancestral gather from the staged row ---------------------------
+        const size_t off5 = cur_off();
+        row = *(volatile int *)&sh.next_row;
         if (!FUSED || p.idx != nullptr) { // (the fused-model step may resample without storing the ancestors)
-            int4 *__restrict__ gidx4 = reinterpret_cast<int4 *>(p.idx + off) + 4 * tid;
+            int4 *__restrict__ gidx4 = reinterpret_cast<int4 *>(p.idx + off5) + 4 * tid;
 #pragma unroll
             for (int i = 0; i < 4; ++i) __stcs(gidx4 + i, make_int4(id[4 * i], id[4 * i + 1], id[4 * i + 2], id[4 * i + 3]));
         }
         if (HAS_X) {
-            float4 *__restrict__ xo4 = reinterpret_cast<float4 *>(p.x_out + off) + 4 * tid;
+            float4 *__restrict__ xo4 = reinterpret_cast<float4 *>(p.x_out + off5) + 4 * tid;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 __stcs(xo4 + i, make_float4(bufX[id[4 * i]], bufX[id[4 * i + 1]], bufX[id[4 * i + 2]], bufX[id[4 * i + 3]]));
