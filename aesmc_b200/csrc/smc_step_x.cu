@@ -144,8 +144,6 @@ __device__ __forceinline__ void mark_run(unsigned marks_s, int cp, int c, int id
                  ::"r"(addr), "r"(c), "r"(cp), "r"(id) : "memory");
 }
 
-// IEEE division out of line (rare paths: keeps eight inlined copies of its range handling out of the instruction cache)
-static __device__ __noinline__ float fdiv_rn_call(float a, float b) { return __fdiv_rn(a, b); }
 
 // the boundary count of common.cuh with the float64 uniform read from shared memory inside the rare fix-up
 static __device__ __noinline__ int count_positions_below_slow_x(float cdf_entry, const double *u_sh, int K)
@@ -161,14 +159,13 @@ static __device__ __noinline__ int count_positions_below_slow_x(float cdf_entry,
 // u_lo = fl32(u - u_hi): 2^-50 absolute error), u_hi - Tf is exact whenever the two are close (Sterbenz), so the
 // sign of d = (u_hi - Tf) + u_lo is the sign of u - Tf unless |d| is below a band of K 2^-46; only then (and for
 // u_hi = 1) the reference's own float64 expression is evaluated (count_positions_below_slow_x).
-__device__ __forceinline__ int count_positions_near_x(float cdfn, float u_hi, const float *u_lo_sh, const double *u_sh,
-                                                      int K, float Kf)
+__device__ __forceinline__ bool count_positions_near_x(float cdfn, float u_hi, const float *u_lo_sh, float Kf, int &count)
 {
     const float T = __fmul_rn(cdfn, Kf);
     const float Ti = floorf(T);
     const float d = __fadd_rn(__fsub_rn(u_hi, __fsub_rn(T, Ti)), *u_lo_sh);
-    if (fabsf(d) > Kf * 1.4210854715202004e-14f && u_hi < 1.0f) return (int)Ti + (d < 0.0f);
-    return count_positions_below_slow_x(cdfn, u_sh, K);
+    count = (int)Ti + (d < 0.0f);
+    return fabsf(d) > Kf * 1.4210854715202004e-14f && u_hi < 1.0f; // false: undecided in float32
 }
 __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry, const double *u_sh, const float *u_lo_sh,
                                                                 float u32, int K, float Kf, float tol32)
@@ -177,7 +174,9 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
     const float tm = __fadd_rn(tf, 12582912.0f);
     const float d = __fsub_rn(tf, __fsub_rn(tm, 12582912.0f)); // tf - rint(tf), exact
     if (fabsf(d) > tol32) return __float_as_int(__fadd_ru(tf, 12582912.0f)) - 0x4B400000; // ceil(tf) <= K
-    return count_positions_near_x(cdf_entry, u32, u_lo_sh, u_sh, K, Kf);
+    int c;
+    if (count_positions_near_x(cdf_entry, u32, u_lo_sh, Kf, c)) return c;
+    return count_positions_below_slow_x(cdf_entry, u_sh, K);
 }
 
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
@@ -219,6 +218,9 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 #ifndef AESMC_X_BULK
 #define AESMC_X_BULK 1 // 1: the latent row is staged by ONE bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA
 #endif                 // engine moves the 4 K bytes, no thread issues a load) instead of four 16-byte cp.async per thread
+#ifndef AESMC_X_FORCE_GENERAL
+#define AESMC_X_FORCE_GENERAL 0 // 1 (test builds): a quarter of the threads leave the call-free boundary loop at its fourth pair
+#endif
 #ifndef AESMC_X_FORCE_FAIL
 #define AESMC_X_FORCE_FAIL 0 // 1 (test builds): every row fails the scan's verification and takes the sequential redo path
 #endif
@@ -712,11 +714,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             float rcp = rcp_approx(total);
             rcp = __fmaf_rn(__fmaf_rn(-total, rcp, 1.0f), rcp, rcp);
             const bool tot_safe = total > 9.3132257e-10f && total < 2.0f;
-            // the CDF is non-decreasing: its first entry bounds the others from below, so one test per thread
-            // decides whether the hoisted-reciprocal division is the IEEE quotient for all 16
-            const bool safe = tot_safe && w[0] >= 7.8886090522101181e-31f;
-            int cp = 0;
-            if (tid != 0 && !AESMC_X_ABLATE) cp = count_positions_below_filtered_x(div_hoisted(s_in, total, rcp, tot_safe), &sh.u64, &sh.ulo, u32, K, Kf, p.tol32);
+            // the CDF is non-decreasing: the entry in front of the thread's block bounds the others from below, so one
+            // test per thread decides whether the hoisted-reciprocal division is the IEEE quotient for all 17
+            const bool safe = tot_safe && (tid ? s_in : w[0]) >= 7.8886090522101181e-31f;
             unsigned marks_s = (unsigned)__cvta_generic_to_shared(bufM);
             asm volatile("" : "+r"(marks_s)); // one register for the whole loop: do not rebuild the shared base per store
             const f32x2 rcp2 = splat2(rcp), ntot2 = splat2(-total), K2 = splat2(Kf), nu2 = splat2(-u32);
@@ -724,18 +724,25 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             const float tol32 = p.tol32;
             int idb = 16 * tid;
             asm volatile("" : "+r"(idb)); // (kept in a register: otherwise the thread index is re-read for every pair)
-            // one warp-uniform choice of the division form for all eight pairs instead of a branch inside every pair
-            auto pairs = [&](auto safe_c) {
+            // THE HOT LOOP HAS NO CALLS: a call site inside it makes the 16 CDF entries live across a call, and all but
+            // the callee-saved few are then spilled for every thread of every row (measured: 4.6 % of the warp time
+            // waiting for those reloads).  Whatever needs an out-of-line routine -- the IEEE division outside the range
+            // the hoisted reciprocal is exact in, the reference's float64 comparison for a boundary within 2^-46 K of
+            // an integer -- leaves the loop for the rolled general loop below, which restarts at the pair it left.
+            int jd = 0, cp = 0;
+            if (__all_sync(kFull, safe)) { // one warp-uniform choice instead of a branch inside every pair
+                if (tid != 0) {
+                    const float q0 = __fmul_rn(s_in, rcp), n = __fmaf_rn(__fmaf_rn(-total, q0, s_in), rcp, q0);
+                    const float tf = __fmaf_rn(n, Kf, -u32);
+                    const float d = __fsub_rn(tf, __fsub_rn(__fadd_rn(tf, 12582912.0f), 12582912.0f));
+                    cp = __float_as_int(__fadd_ru(tf, 12582912.0f)) - 0x4B400000;
+                    if (!(fabsf(d) > tol32) && !count_positions_near_x(n, u32, &sh.ulo, Kf, cp)) goto general;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
-                    f32x2 n2;
-                    if (decltype(safe_c)::value) {
-                        const f32x2 c2 = pack2(w[j], w[j + 1]);
-                        const f32x2 q0 = mul2(c2, rcp2);
-                        n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
-                    } else {
-                        n2 = pack2(fdiv_rn_call(w[j], total), fdiv_rn_call(w[j + 1], total));
-                    }
+                    const f32x2 c2 = pack2(w[j], w[j + 1]);
+                    const f32x2 q0 = mul2(c2, rcp2);
+                    const f32x2 n2 = fma2(fma2(ntot2, q0, c2), rcp2, q0);
                     const f32x2 tf = fma2(n2, K2, nu2);         // cdfn * K - u, one rounding; <= K because cdfn <= 1
                     const f32x2 tm = add2(tf, magic);
                     const f32x2 d2 = sub2(tf, sub2(tm, magic)); // tf - rint(tf), exact
@@ -747,20 +754,34 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     unpack2(tmu, m0, m1);
                     int ca = __float_as_int(m0) - 0x4B400000;
                     int cb = __float_as_int(m1) - 0x4B400000;
-                    if (!(AESMC_X_ABLATE & 8) && !(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
+                    if (AESMC_X_FORCE_GENERAL && j == 6 && (tid & 3) == 1) { jd = j; goto general; }
+                    if (!(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
                         float n0, n1;
                         unpack2(n2, n0, n1);
-                        if (!(fabsf(d0) > tol32)) ca = count_positions_near_x(n0, u32, &sh.ulo, &sh.u64, K, Kf);
-                        if (!(fabsf(d1) > tol32)) cb = count_positions_near_x(n1, u32, &sh.ulo, &sh.u64, K, Kf);
+                        if (!(fabsf(d0) > tol32) && !count_positions_near_x(n0, u32, &sh.ulo, Kf, ca)) { jd = j; goto general; }
+                        if (!(fabsf(d1) > tol32) && !count_positions_near_x(n1, u32, &sh.ulo, Kf, cb)) { jd = j; goto general; }
                     }
-                    if (AESMC_X_ABLATE) { ca = min(max(ca, cp), K); cb = min(max(cb, ca), K); }
                     if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
                     mark_run(marks_s, cp, ca, idb + j);
                     mark_run(marks_s, ca, cb, idb + j + 1);
                     cp = cb;
                 }
-            };
-            if (__all_sync(kFull, safe)) pairs(std::true_type{}); else pairs(std::false_type{});
+                jd = 16;
+            }
+        general:
+            if (jd < 16) { // (a whole warp of a row with collapsed weights, else single lanes about once per 10^7 particles)
+                float wl[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) wl[j] = w[j];
+                if (jd == 0) cp = tid ? count_positions_below_filtered_x(__fdiv_rn(s_in, total), &sh.u64, &sh.ulo, u32, K, Kf, tol32) : 0;
+#pragma unroll 1
+                for (int j = jd; j < 16; ++j) {
+                    int c = count_positions_below_filtered_x(__fdiv_rn(wl[j], total), &sh.u64, &sh.ulo, u32, K, Kf, tol32);
+                    if (j == 15 && tid == NT - 1) c = K;
+                    mark_run(marks_s, cp, c, idb + j);
+                    cp = c;
+                }
+            }
             if (kBulkX) {
                 if (attempt == 0) mbar_wait(&xbar, *(volatile unsigned *)&sh.xphase);
             } else if (HAS_X && !FUSED) {
