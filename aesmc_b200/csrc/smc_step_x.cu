@@ -624,19 +624,20 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 }
                 const int carry_in = carry;
                 int s_own = 0;
-                for (unsigned m = (AESMC_X_ABLATE & 1) ? 0u : opqmask; m; m &= m - 1) { // the serial part of the row: ~10 mixed blocks
-                    // (fetching the next block while this one's additions run was measured: the extra registers spill,
-                    // and local-memory round trips on this lone warp cost more than the shuffle + load they hide)
+                // the serial part of the row, ~10 mixed blocks: every lane holds ITS record's block in registers (one round
+                // of loads for all of them, off the chain) and every lane runs every step on its own block and map; only
+                // lane pl's result is the chain's, and one shuffle hands it to the next step: 16 additions + 1 shuffle of
+                // latency per mixed block instead of three shuffles, four shared-memory loads and the additions
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+                if (opq) { v0 = bufW4[rblk]; v1 = bufW4[rblk + 1]; v2 = bufW4[rblk + 2]; v3 = bufW4[rblk + 3]; }
+                for (unsigned m = (AESMC_X_ABLATE & 1) ? 0u : opqmask; m; m &= m - 1) {
                     const int pl = __ffs(m) - 1;
-                    const int m0 = __shfl_sync(kFull, C0, pl), m1 = __shfl_sync(kFull, C1, pl);
-                    const int blk = __shfl_sync(kFull, rblk, pl);
-                    const float4 v0 = bufW4[blk], v1 = bufW4[blk + 1], v2 = bufW4[blk + 2], v3 = bufW4[blk + 3];
-                    float s = __int_as_float(carry + ((carry & 1) ? m1 : m0));
+                    float s = __int_as_float(carry + ((carry & 1) ? C1 : C0));
                     s = __fadd_rn(s, v0.x); s = __fadd_rn(s, v0.y); s = __fadd_rn(s, v0.z); s = __fadd_rn(s, v0.w);
                     s = __fadd_rn(s, v1.x); s = __fadd_rn(s, v1.y); s = __fadd_rn(s, v1.z); s = __fadd_rn(s, v1.w);
                     s = __fadd_rn(s, v2.x); s = __fadd_rn(s, v2.y); s = __fadd_rn(s, v2.z); s = __fadd_rn(s, v2.w);
                     s = __fadd_rn(s, v3.x); s = __fadd_rn(s, v3.y); s = __fadd_rn(s, v3.z); s = __fadd_rn(s, v3.w);
-                    carry = __float_as_int(s);
+                    carry = __shfl_sync(kFull, __float_as_int(s), pl);
                     if (lane == pl) s_own = carry;
                 }
                 // chain value after every record: its own for a mixed block, else the run's map applied to the value
