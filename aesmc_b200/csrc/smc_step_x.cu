@@ -179,6 +179,20 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
     return count_positions_below_slow_x(cdf_entry, u_sh, K);
 }
 
+// the warp chain of level 2: one 8-byte shared-memory word per warp, (value, tag), written and read as a unit
+__device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
+{
+    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(value), "r"(tag) : "memory");
+}
+__device__ __forceinline__ int chain_wait(unsigned addr, int tag)
+{
+    int v, t;
+    do {
+        asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "r"(addr) : "memory");
+    } while (t != tag);
+    return v;
+}
+
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]
 __device__ __forceinline__ void compose(int p0, int p1, int n0, int n1, int &h0, int &h1)
 {
@@ -193,10 +207,10 @@ template <int NW> struct Shared {
     double u64;               // this row's uniform (read by the rarest fix-up of the boundary count)
     float ulo;                // u64 - fl32(u64) (read by the rare float32 fix-up)
     float wmax[NW], part[NW], wsum[NW];
-    int cnt[NW], nrec[NW], i2[NW];
+    int cnt[NW], i2[NW];
     float lse, total;
     int bad, fail;
-    float seg_state[NW * 32]; // exact chain value [warp][k]: entering the warp's span (k = 0), after its k-th mixed block
+    int2 chain[NW + 1];       // (bits of the exact chain value entering warp w's span, row tag); [NW]: the row's total
 };
 
 template <int NW> __device__ __forceinline__ float across_max(const float *arr, int lane)
@@ -258,9 +272,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     // [NW][32] records of the exact scan, written by every warp, read by the walker warp: (c0, mixed block's chunk + 1
     // or 0 | (c1 - c0 + 1) << 16) -- the two entries of a parity map differ by -1, 0 or 1 (two chains that start one
     // unit apart stay 0, 1 or 2 units apart: round-to-nearest shifts both alike except at ties)
-    int2 *seg_rec = reinterpret_cast<int2 *>(bufM4 + ROWCH + ((HAS_X && !AESMC_X_ALIAS_X) ? NCH : 0));
     __shared__ Shared<NW> sh;
-    float *seg_state = sh.seg_state;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wbase = 144 * warp;                 // the warp's 128 chunks (+16 spare) of a padded row
@@ -275,6 +287,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     if (tid == 0) {
         sh.bad = 0;
         sh.xphase = 0;
+        for (int i = 0; i <= NW; ++i) sh.chain[i] = make_int2(0, 0); // (tags are row + 1: never 0)
         if (kBulkX) mbar_init(&xbar, 1);
     }
     __syncthreads();
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (bad) sh.bad = 1;
         }
         __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
-        if (tid == 0) { sh.cur_row = row; sh.next_row = row + (int)gridDim.x; }
+        if (tid == 0) { sh.cur_row = row; sh.next_row = row + (int)gridDim.x; sh.fail = 0; }
         if (HAS_X && !FUSED && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
@@ -499,7 +512,18 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (lane >= o) incl += n;
         }
         if (lane == 31) sh.wsum[warp] = incl;
-        __syncthreads(); // (4) warp totals of the approximate prefix
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // run marks of P4 (the previous row's readers are past barrier (1))
+        __syncthreads(); // (4) warp totals of the approximate prefix; run marks cleared; every warp holds its weights in registers
+        if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
+            if (kBulkX) { // one bulk copy (issued by one thread, completion on the mbarrier waited for in front of barrier (8))
+                if (tid == 0) bulk_copy_g2s(bufX4, p.x_in + cur_off(), (unsigned)K * 4u, &xbar);
+            } else {
+                const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + cur_off()) + gc;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
+            }
+        }
         float woff;
         {
             float sc = sh.wsum[lane & (NW - 1)];
@@ -559,132 +583,44 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         }
         int prev0 = __shfl_up_sync(kFull, g0, 1), prev1 = __shfl_up_sync(kFull, g1, 1); // map of the run before this block
         if (lane == 0) prev0 = prev1 = 0;
-        // records for level 2, in particle order: one per mixed block (the map of the run in front of it, then the
-        // block itself) and one for the run that ends the warp's span
-        if (mixed) seg_rec[32 * warp + kmix] = make_int2(prev0, (bl + 1) | ((prev1 - prev0 + 1) << 16));
-        if (lane == 31) {
-            const int nmix = __popc(mixmask);
-            if (!mixed) seg_rec[32 * warp + nmix] = make_int2(g0, (g1 - g0 + 1) << 16);
-            sh.nrec[warp] = nmix + (mixed ? 0 : 1);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // run marks of P4 (the previous row's readers are past barrier (1))
-        __syncthreads(); // (5) records
-        if ((AESMC_X_ABLATE & 2) ? (tid == 0) : (warp == NW - 1)) {
-            if (AESMC_X_ABLATE & 2) { sh.total = 1.0f; sh.fail = 0; } else {
-            // Level 2, one warp, lane = record: the maps between two mixed blocks compose by a segmented shuffle scan;
-            // only the mixed blocks themselves (16 real additions each) are walked one after the other.  Verification
-            // is not done here: every block re-checks, in parallel, that its entry value and its partial sums stayed
-            // inside the assumed binade (replay below), which covers every step taken here.
-            // lane -> record.  Usual case: no warp has more than four records, lane = 4 * (warp mod 8) + record, eight
-            // warps per pass (empty slots are identity records); otherwise the lists are compacted by a prefix sum.
-            const int n_l = sh.nrec[lane & (NW - 1)];
-            const bool slots = __all_sync(kFull, n_l <= 4);
-            int pre = n_l;
-            if (!slots) {
-#pragma unroll
-                for (int o = 1; o < NW; o <<= 1) {
-                    const int t = __shfl_up_sync(kFull, pre, o);
-                    if (lane >= o) pre += t;
-                }
-            }
-            const int R = slots ? 4 * NW : __shfl_sync(kFull, pre, NW - 1);
-            const int start = pre - n_l; // (compacted lists) first record of warp `lane` in particle order
-            int carry = 0;               // bits of the chain value (0.0f at the start of a row)
-            if (lane == 0) seg_state[0] = 0.f;
-            for (int base = 0; base < R; base += 32) {
-                int wi, r, n_wi;
-                bool valid;
-                if (slots) {
-                    wi = (base >> 2) + (lane >> 2);
-                    r = lane & 3;
-                    n_wi = sh.nrec[wi & (NW - 1)];
-                    valid = wi < NW && r < n_wi;
-                } else {
-                    const int gi = base + lane;
-                    const bool starts_here = lane < NW && start >= base && start < base + 32;
-                    const unsigned startmask = __reduce_or_sync(kFull, starts_here ? (1u << (start - base)) : 0u);
-                    const int nbefore = __popc(__ballot_sync(kFull, lane < NW && start < base));
-                    wi = __popc(startmask & ((2u << lane) - 1u)) + nbefore - 1; // the warp record gi belongs to
-                    n_wi = __shfl_sync(kFull, n_l, wi);
-                    r = gi - __shfl_sync(kFull, start, wi);
-                    valid = gi < R;
-                }
-                const int2 rec = valid ? seg_rec[32 * wi + r] : make_int2(0, 1 << 16);
-                const int rblk = (rec.y & 0xffff) - 1; // first padded chunk of the record's mixed block, -1: none
-                const bool opq = rblk >= 0;
-                const unsigned opqmask = __ballot_sync(kFull, opq);
-                // a record starts a new run iff the one before it ends with a mixed block
-                const int dist = lane - (31 - __clz(((opqmask << 1) | 1u) & ((2u << lane) - 1u)));
-                int C0 = rec.x, C1 = rec.x + (rec.y >> 16) - 1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int q0 = __shfl_up_sync(kFull, C0, o), q1 = __shfl_up_sync(kFull, C1, o);
-                    if (o <= dist) compose(q0, q1, C0, C1, C0, C1);
-                }
-                const int carry_in = carry;
-                int s_own = 0;
-                // the serial part of the row, ~10 mixed blocks: every lane holds ITS record's block in registers (one round
-                // of loads for all of them, off the chain) and every lane runs every step on its own block and map; only
-                // lane pl's result is the chain's, and one shuffle hands it to the next step: 16 additions + 1 shuffle of
-                // latency per mixed block instead of three shuffles, four shared-memory loads and the additions
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-                if (opq) { v0 = bufW4[rblk]; v1 = bufW4[rblk + 1]; v2 = bufW4[rblk + 2]; v3 = bufW4[rblk + 3]; }
-                for (unsigned m = (AESMC_X_ABLATE & 1) ? 0u : opqmask; m; m &= m - 1) {
+        // Level 2, a chain over the warps of the CTA instead of a walker warp behind two barriers: warp w waits for the
+        // exact chain value E_w entering its span (published by warp w - 1 in shared memory, tagged with the row),
+        // pushes it through its own blocks and publishes E_{w+1}.  A warp without mixed blocks -- all but the first
+        // one or two of a typical row -- forwards E_w through the map of its 32 blocks: three integer instructions
+        // between the poll that sees E_w and the store of E_{w+1}.  Only mixed blocks are walked (16 real additions each,
+        // every lane on its own registers, one shuffle per block).  seg = chain value after the last mixed block in
+        // front of a lane (E_w if there is none); the replay below starts from it.
+        int seg;
+        {
+            const int tag = *(volatile int *)&sh.cur_row + 1;
+            const unsigned chain_s = (unsigned)__cvta_generic_to_shared(sh.chain);
+            int E = 0;
+            if (mixmask == 0u) {
+                const int G0 = __shfl_sync(kFull, g0, 31), G1 = __shfl_sync(kFull, g1, 31);
+                if (warp) E = chain_wait(chain_s + 8u * warp, tag);
+                const int ex = E + ((E & 1) ? G1 : G0);
+                if (lane == 0) chain_publish(chain_s + 8u * (warp + 1), ex, tag);
+                seg = E;
+            } else {
+                if (warp) E = chain_wait(chain_s + 8u * warp, tag);
+                int carry = E, t = 0;
+                seg = E;
+                for (unsigned m = mixmask; m; m &= m - 1) {
                     const int pl = __ffs(m) - 1;
-                    float s = __int_as_float(carry + ((carry & 1) ? C1 : C0));
-                    s = __fadd_rn(s, v0.x); s = __fadd_rn(s, v0.y); s = __fadd_rn(s, v0.z); s = __fadd_rn(s, v0.w);
-                    s = __fadd_rn(s, v1.x); s = __fadd_rn(s, v1.y); s = __fadd_rn(s, v1.z); s = __fadd_rn(s, v1.w);
-                    s = __fadd_rn(s, v2.x); s = __fadd_rn(s, v2.y); s = __fadd_rn(s, v2.z); s = __fadd_rn(s, v2.w);
-                    s = __fadd_rn(s, v3.x); s = __fadd_rn(s, v3.y); s = __fadd_rn(s, v3.z); s = __fadd_rn(s, v3.w);
+                    float s = __int_as_float(carry + ((carry & 1) ? prev1 : prev0));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) s = __fadd_rn(s, w[j]);
                     carry = __shfl_sync(kFull, __float_as_int(s), pl);
-                    if (lane == pl) s_own = carry;
+                    ++t;
+                    if (kmix == t) seg = carry;
                 }
-                // chain value after every record: its own for a mixed block, else the run's map applied to the value
-                // after the last mixed block in front of it
-                const unsigned before = opqmask & lt_mask;
-                int sg = __shfl_sync(kFull, s_own, (31 - __clz(before)) & 31);
-                if (!before) sg = carry_in;
-                const int after = opq ? s_own : sg + ((sg & 1) ? C1 : C0);
-                if (valid) {
-                    const int slot = (r == n_wi - 1) ? 32 * (wi + 1) : 32 * wi + r + 1;
-                    if (slot < 32 * NW) seg_state[slot] = __int_as_float(after);
-                }
-                carry = __shfl_sync(kFull, after, 31);
+                if (lane == 31) chain_publish(chain_s + 8u * (warp + 1), mixed ? carry : seg + ((seg & 1) ? g1 : g0), tag);
             }
-            if (lane == 0) {
-                sh.total = __int_as_float(carry);
-                sh.fail = 0;
-            }
-            }
-            // this warp's own weights are dead while it walks (their registers hold the mixed blocks; the assignment tells
-            // the compiler so) and are reloaded after the barrier
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = 0.f;
-        }
-        __syncthreads(); // (6) exact chain value at every run start
-        if (warp == NW - 1) {
-            // Safe after the barrier: the other warps stage latents into chunks below 128 (NW - 1) of the weight buffer,
-            // this warp's padded slice starts at 144 (NW - 1), and its own staging is issued after the __syncwarp.
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = bufW4[bl + i];
-                w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-            __syncwarp();
-            // the weight buffer is free: one bulk copy stages this row's latents into it for the gather in P5 (issued
-            // here, by the warp whose reload above was the buffer's last reader)
-            if (kBulkX && lane == 0) bulk_copy_g2s(bufX4, p.x_in + cur_off(), (unsigned)K * 4u, &xbar);
-        }
-        if (HAS_X && !FUSED && AESMC_X_ALIAS_X && !kBulkX) { // the weight buffer is free: stage this row's latents into it for the gather in P5
-            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + cur_off()) + gc;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
         }
         float s_in; // exact chain value entering this thread's block = the CDF entry of the particle before it
         {   // every thread replays its own block from its exact entry state
             int badv = 0;
-            int sb = __float_as_int(seg_state[32 * warp + kmix]);
+            int sb = seg;
             sb += (sb & 1) ? prev1 : prev0;
             s_in = __int_as_float(sb);
             if (eb > 0) {
@@ -706,7 +642,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (AESMC_X_FORCE_FAIL) badv = 1;
             if (badv && !(AESMC_X_ABLATE & 16)) sh.fail = 1; // read after barrier (8)
         }
-        float total = sh.total;
+        // the row's total = the chain value leaving the last warp (every warp's marks of P4 were zeroed in front of
+        // barrier (4))
+        float total = __int_as_float(chain_wait((unsigned)__cvta_generic_to_shared(sh.chain) + 8u * NW, *(volatile int *)&sh.cur_row + 1));
 
         // ---- P4: closed-form offspring boundaries (inference.py:251,260-264) and run marks ---------------------
         // particle j owns the positions [c_{j-1}, c_j); the boundary of the particle in front of this thread's block
@@ -916,8 +854,7 @@ static int launch_x(const XStepParams &p, int64_t B, cudaStream_t stream)
 {
     constexpr int NCH = 4 * NT;
     constexpr size_t smem = (size_t)(NCH + NCH / 8) * 16 * 2 +
-                            ((HAS_X && !XConfig<HAS_X, FUSED>::kAlias) ? (size_t)NCH * 16 : 0) +
-                            (size_t)(NT / 32) * 32 * 8; // weights | run marks | [latents] | scan records
+                            ((HAS_X && !XConfig<HAS_X, FUSED>::kAlias) ? (size_t)NCH * 16 : 0); // weights | run marks | [latents]
     auto kern = smc_step_x_kernel<NT, HAS_X, FUSED>;
     static int per_sm = 0;
     if (per_sm == 0) {
