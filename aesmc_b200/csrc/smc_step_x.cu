@@ -179,6 +179,9 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
     return count_positions_below_slow_x(cdf_entry, u_sh, K);
 }
 
+#ifndef AESMC_X_CHAIN_SLEEP
+#define AESMC_X_CHAIN_SLEEP 0 // > 0: nanoseconds of back-off between two polls of the level-2 hand-off
+#endif
 // the warp chain of level 2: one 8-byte shared-memory word per warp, (value, tag), written and read as a unit
 __device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
 {
@@ -187,9 +190,13 @@ __device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
 __device__ __forceinline__ int chain_wait(unsigned addr, int tag)
 {
     int v, t;
-    do {
+    for (;;) {
         asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "r"(addr) : "memory");
-    } while (t != tag);
+        if (t == tag) break;
+#if AESMC_X_CHAIN_SLEEP
+        __nanosleep(AESMC_X_CHAIN_SLEEP);
+#endif
+    }
     return v;
 }
 
@@ -552,17 +559,23 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         }
         const float scale = __int_as_float((277 - (eb > 0 ? eb : 127)) << 23); // 2^(23 - e)
         int c0 = 0, c1 = 0;
-        if (eb > 0) {
+        if (eb > 0) { // from here on a pure block holds its weights SCALED to units of the binade's ulp (exact: powers of two)
             f32x2 m01 = pack2(8388608.0f, 8388609.0f);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m01 = add2(m01, splat2(__fmul_rn(w[j], scale)));
+            for (int j = 0; j < 16; ++j) {
+                w[j] = __fmul_rn(w[j], scale);
+                m01 = add2(m01, splat2(w[j]));
+            }
             float m0, m1;
             unpack2(m01, m0, m1);
             if (m1 < 16777216.0f) {
                 c0 = __float_as_int(m0) & 0x7fffff;
                 c1 = (__float_as_int(m1) & 0x7fffff) - 1;
-            } else {
+            } else { // the block may leave the binade after all: mixed, on its unscaled weights again
                 eb = 0;
+                const float back = __int_as_float((254 << 23) - __float_as_int(scale)); // 1 / scale
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = __fmul_rn(w[j], back);
             }
         }
         // Level 1 (inside the warp): parity maps of consecutive non-mixed blocks compose (on the BIT PATTERN of the chain
@@ -630,7 +643,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 const int unscale = (150 - eb) << 23;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    mf = __fadd_rn(mf, __fmul_rn(w[j], scale));
+                    mf = __fadd_rn(mf, w[j]);
                     w[j] = __int_as_float(__float_as_int(mf) - unscale);
                 }
                 if (mf > 16777216.0f) badv = 1;
