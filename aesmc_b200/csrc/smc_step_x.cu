@@ -183,21 +183,38 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
 #define AESMC_X_CHAIN_SLEEP 0 // > 0: nanoseconds of back-off between two polls of the level-2 hand-off
 #endif
 // the warp chain of level 2: one 8-byte shared-memory word per warp, (value, tag), written and read as a unit
+#ifndef AESMC_X_CHAIN_SYNC
+#define AESMC_X_CHAIN_SYNC 1 // 0: volatile accesses, 1: st.release / ld.acquire at CTA scope, 2: shared-memory atomics
+#endif
 __device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
 {
-    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(value), "r"(tag) : "memory");
+    const unsigned long long rec = ((unsigned long long)(unsigned)tag << 32) | (unsigned)value;
+#if AESMC_X_CHAIN_SYNC == 0
+    asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(addr), "l"(rec) : "memory");
+#elif AESMC_X_CHAIN_SYNC == 1
+    asm volatile("st.release.cta.shared.b64 [%0], %1;" ::"r"(addr), "l"(rec) : "memory");
+#else
+    unsigned long long old;
+    asm volatile("atom.shared.exch.b64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(rec) : "memory");
+#endif
 }
 __device__ __forceinline__ int chain_wait(unsigned addr, int tag)
 {
-    int v, t;
+    unsigned long long rec;
     for (;;) {
-        asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "r"(addr) : "memory");
-        if (t == tag) break;
+#if AESMC_X_CHAIN_SYNC == 0
+        asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(rec) : "r"(addr) : "memory");
+#elif AESMC_X_CHAIN_SYNC == 1
+        asm volatile("ld.acquire.cta.shared.b64 %0, [%1];" : "=l"(rec) : "r"(addr) : "memory");
+#else
+        asm volatile("atom.shared.or.b64 %0, [%1], 0;" : "=l"(rec) : "r"(addr) : "memory");
+#endif
+        if ((int)(rec >> 32) == tag) break;
 #if AESMC_X_CHAIN_SLEEP
         __nanosleep(AESMC_X_CHAIN_SLEEP);
 #endif
     }
-    return v;
+    return (int)(unsigned)rec;
 }
 
 // (prev then next): H[p] = P[p] + N[(p + P[p]) & 1]

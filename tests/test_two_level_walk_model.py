@@ -3,14 +3,16 @@ on the CPU against the sequential float32 chain (np.cumsum, inference.py:257).
 
 What the kernel does per row of K = 16 * NT particles (block = a thread's 16 particles, warp = 32 blocks):
   level 1  inside a warp: the parity maps (c0, c1) of consecutive non-mixed blocks compose ON THE BIT PATTERN of the
-           chain value (bits + c[bits & 1]); a mixed block cuts the run.  Each warp emits, in particle order, one record
-           per mixed block (the map of the run in front of it, then the block) and one for the run that ends its span.
-  level 2  one warp, lane = record: the maps between two mixed blocks compose by a segmented scan; only the mixed blocks
-           (16 real additions each) are walked serially; the value after every record is scattered to seg_state[warp][k]
-           (k = 0: entering the warp's span, k >= 1: after its k-th mixed block).
-  replay   every block starts from seg_state[warp][#mixed blocks before it] pushed through the map of the run in front of
-           it, and must land on the true chain value.
-The records are packed as (c0, c1 - c0 + 1): two chains that start one unit apart stay 0, 1 or 2 units apart.
+           chain value (bits + c[bits & 1]); a mixed block cuts the run.  Every lane ends up with the map of the run in
+           front of its block (prev) and of the run through its block (g).
+  level 2  a chain over the warps: warp w receives the exact chain value E_w entering its span from warp w - 1 (a tagged
+           shared-memory word), and hands E_{w+1} on.  A warp without mixed blocks forwards E_w through the map of its
+           32 blocks; otherwise only its mixed blocks (16 real additions each) are walked one after the other.
+           seg = chain value after the last mixed block in front of a lane (E_w if there is none).
+  replay   every block starts from seg pushed through the map of the run in front of it, and must land on the true
+           chain value.
+Two chains that start one unit apart stay 0, 1 or 2 units apart (the kernel never stores c1 - c0 any more, the model
+still checks it).
 """
 import numpy as np
 import pytest
@@ -73,52 +75,38 @@ def classify(w):
 
 
 def two_level_entry_states(w):
-    """Entry value (bit pattern) of every block as the kernel derives it; also returns the record count."""
+    """Entry value (bit pattern) of every block as the kernel derives it; also returns the number of serial steps."""
     blocks, kinds, maps = classify(w)
     nb = len(kinds)
     nw = (nb + 31) // 32
-    # ---- level 1 -------------------------------------------------------------------------------------------
-    prev_map, kmix, records = [None] * nb, [0] * nb, []
+    entry, steps = [0] * nb, 0
+    E = 0                                        # bits of the chain value entering warp 0's span: 0.0f
     for wi in range(nw):
-        run, k, recs = (0, 0), 0, []
-        for b in range(32 * wi, min(32 * wi + 32, nb)):
-            prev_map[b], kmix[b] = run, k
-            if kinds[b] == 0:
-                recs.append((run, b))           # the map of the run in front of the mixed block, then the block
-                assert -1 <= run[1] - run[0] <= 1
-                run, k = (0, 0), k + 1
-            else:
-                run = compose(run, maps[b])      # absorbed blocks carry (0, 0)
-        if kinds[min(32 * wi + 31, nb - 1)] != 0:
-            recs.append((run, -1))
+        lanes = range(32 * wi, min(32 * wi + 32, nb))
+        # ---- level 1: per lane, the map of the run in front of the block (prev) and through it (g) -------------
+        run, prev, g = (0, 0), {}, {}
+        for b in lanes:
+            prev[b] = run
             assert -1 <= run[1] - run[0] <= 1
-        records.append(recs)
-    # ---- level 2: lane = record, 32 per pass; segmented scan between mixed blocks, mixed blocks serial ---------
-    flat = [(wi, r, rec) for wi, recs in enumerate(records) for r, rec in enumerate(recs)]
-    seg_state = {(0, 0): 0}
-    carry = 0
-    for base in range(0, len(flat), 32):
-        chunk = flat[base:base + 32]
-        comp, head = [], True
-        for (_, _, (m, blk)) in chunk:           # inclusive composed map of each record's run of maps
-            comp.append(m if head else compose(comp[-1], m))
-            head = blk >= 0
-        s_own, after_last, carry_in = {}, None, carry
-        for i, (_, _, (m, blk)) in enumerate(chunk):
-            if blk >= 0:                         # the serial part
-                s = from_bits(apply_map(carry, comp[i]))
-                carry = bits(seq_sum(blocks[blk], s))
-                s_own[i] = carry
-        for i, (wi, r, (m, blk)) in enumerate(chunk):
-            prior = [j for j in s_own if j < i]
-            sg = s_own[max(prior)] if prior else carry_in
-            after = s_own[i] if blk >= 0 else apply_map(sg, comp[i])
-            last = r == len(records[wi]) - 1
-            seg_state[(wi + 1, 0) if last else (wi, r + 1)] = after
-            after_last = after
-        carry = after_last
-    entry = [apply_map(seg_state[(b // 32, kmix[b])], prev_map[b]) for b in range(nb)]
-    return entry, kinds, len(flat), carry
+            run = (0, 0) if kinds[b] == 0 else compose(run, maps[b])   # absorbed blocks carry (0, 0)
+            g[b] = run
+        # ---- level 2: E_w -> seg of every lane -> E_{w+1} --------------------------------------------------------
+        seg = {b: E for b in lanes}
+        carry = E
+        for b in lanes:
+            if kinds[b] == 0:                    # the serial part: one step per mixed block
+                s = from_bits(apply_map(carry, prev[b]))
+                carry = bits(seq_sum(blocks[b], s))
+                steps += 1
+                for later in lanes:
+                    if later > b:
+                        seg[later] = carry
+        last = lanes[-1]
+        for b in lanes:
+            entry[b] = apply_map(seg[b], prev[b])
+        E = carry if kinds[last] == 0 else apply_map(seg[last], g[last])
+        steps += 1                               # the hand-off to the next warp
+    return entry, kinds, steps, E
 
 
 @pytest.mark.parametrize("K", [1024, 4096, 16384])
@@ -144,5 +132,5 @@ def test_two_level_walk_reproduces_the_sequential_chain(K):
         nrec += n
         nmixed += sum(k == 0 for k in kinds)
         nrows += 1
-    # the level-2 warp sees a few dozen records per row, not one per block
-    assert nrec / nrows < 8 + 2.5 * (nmixed / nrows) + K / 512
+    # the serial part of a row is one step per mixed block and one hand-off per warp, not one per block
+    assert nrec / nrows <= nmixed / nrows + K / 512
