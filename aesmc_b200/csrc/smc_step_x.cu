@@ -139,7 +139,9 @@ __device__ __forceinline__ void sts_b32(unsigned addr, int v) { asm volatile("st
 // cycles per scheduler, is what bounds this kernel); byte offset of pad_elem(cp): 4 cp + 16 (cp >> 5)
 __device__ __forceinline__ void mark_run(unsigned marks_s, int cp, int c, int id)
 {
-    const unsigned addr = marks_s + 4 * cp + ((cp >> 5) << 4);
+    int hi; // cp >> 5, opaque to the compiler: (cp >> 5) << 4 would become (cp >> 1) & ~15 and cost a fourth instruction
+    asm("shr.s32 %0, %1, 5;" : "=r"(hi) : "r"(cp));
+    const unsigned addr = (marks_s + 4 * cp) + 16 * hi; // two shift-and-add instructions
     asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %1, %2;\n\t@p st.shared.b32 [%0], %3;\n\t}"
                  ::"r"(addr), "r"(c), "r"(cp), "r"(id) : "memory");
 }
