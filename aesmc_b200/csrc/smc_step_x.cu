@@ -258,6 +258,18 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 #ifndef AESMC_X_BULK
 #define AESMC_X_BULK 1 // 1: the latent row is staged by ONE bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA
 #endif                 // engine moves the 4 K bytes, no thread issues a load) instead of four 16-byte cp.async per thread
+#ifndef AESMC_X_ARRIVE4
+#define AESMC_X_ARRIVE4 1 // 1: warp 0 arrives at barrier (4) without waiting (see there)
+#endif
+#ifndef AESMC_X_TIMELINE
+#define AESMC_X_TIMELINE 0 // 1 (profiling builds): per-warp clock stamps of the phases of CTA 0's rows, read by aesmc_debug_timeline
+#endif
+#if AESMC_X_TIMELINE
+__device__ long long g_timeline[32 * 16]; // [warp][stage]: cycles since the row's start, summed over CTA 0's rows; [.][15] = rows
+#define TL(stage) do { if (blockIdx.x == 0 && lane == 0) g_timeline[16 * warp + (stage)] += clock64() - tl0; } while (0)
+#else
+#define TL(stage) do { } while (0)
+#endif
 #ifndef AESMC_X_FORCE_GENERAL
 #define AESMC_X_FORCE_GENERAL 0 // 1 (test builds): a quarter of the threads leave the call-free boundary loop at its fourth pair
 #endif
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     const float Kf = (float)K;
 
     constexpr bool kBulkX = AESMC_X_BULK && HAS_X && !FUSED && AESMC_X_ALIAS_X;
+    constexpr bool kArrive4 = AESMC_X_ARRIVE4 && NT > 32 && (kBulkX || !(HAS_X && !FUSED && AESMC_X_ALIAS_X));
     __shared__ __align__(8) unsigned long long xbar; // completion of the latent row's bulk copy
     if (tid == 0) {
         sh.bad = 0;
@@ -322,6 +335,10 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     int row = blockIdx.x;
     while (row < p.B) {
         const size_t off = (size_t)row * K; // P1 only: later phases use cur_off()
+#if AESMC_X_TIMELINE
+        const long long tl0 = clock64();
+        if (blockIdx.x == 0 && lane == 0) g_timeline[16 * warp + 15] += 1;
+#endif
         const float u32 = (float)p.u[row];
         if (tid == 0) { // (visible after barrier (1); the last readers are in front of the previous row's barrier (8))
             const double ud = p.u[row];
@@ -404,7 +421,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (lane == 0) sh.wmax[warp] = wm;
             if (bad) sh.bad = 1;
         }
+        TL(0);
         __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
+        TL(1);
         if (tid == 0) { sh.cur_row = row; sh.next_row = row + (int)gridDim.x; sh.fail = 0; }
         if (HAS_X && !FUSED && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
@@ -473,7 +492,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (__any_sync(kFull, has_max)) cnt = warp_sum(cnt);
             if (lane == 0) { sh.part[warp] = r; sh.cnt[warp] = cnt; }
         }
+        TL(2);
         __syncthreads(); // (2) per-warp partial sums and maxima counts
+        TL(3);
         float lse;
         if (AESMC_X_REDUNDANT_TAIL || warp == NW - 1) { // fold the partials and evaluate the scalar tail (division, log1p, log)
             float s = sh.part[lane & (NW - 1)];
@@ -540,18 +561,26 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         if (lane == 31) sh.wsum[warp] = incl;
 #pragma unroll
         for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0); // run marks of P4 (the previous row's readers are past barrier (1))
-        __syncthreads(); // (4) warp totals of the approximate prefix; run marks cleared; every warp holds its weights in registers
+        TL(4);
+        // (4) warp totals of the approximate prefix; run marks cleared; every warp holds its weights in registers.
+        // Warp 0 only ARRIVES: it needs nothing from the others here (its prefix offset is 0, it touches the marks and
+        // the staged row again only after the row's total is known, which every other warp's pass of this barrier
+        // precedes), and its walk of the row's first mixed blocks is the head of level 2's serial chain.
+        if (kArrive4 && warp == 0) asm volatile("bar.arrive 0, %0;" ::"n"(NT) : "memory");
+        else if (kArrive4) asm volatile("bar.sync 0, %0;" ::"n"(NT) : "memory");
+        else __syncthreads();
+        TL(5);
         if (HAS_X && !FUSED && AESMC_X_ALIAS_X) { // the weight buffer is free: stage this row's latents into it for the gather in P5
             if (kBulkX) { // one bulk copy (issued by one thread, completion on the mbarrier waited for in front of barrier (8))
-                if (tid == 0) bulk_copy_g2s(bufX4, p.x_in + cur_off(), (unsigned)K * 4u, &xbar);
+                if (tid == NT - 32) bulk_copy_g2s(bufX4, p.x_in + cur_off(), (unsigned)K * 4u, &xbar);
             } else {
                 const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + cur_off()) + gc;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cp_async_16(bufX4 + gc + 32 * i, x4 + 32 * i);
             }
         }
-        float woff;
-        {
+        float woff = 0.f;
+        if (warp != 0) { // (warp 0 may be here before the others have stored their totals)
             float sc = sh.wsum[lane & (NW - 1)];
 #pragma unroll
             for (int o = 1; o < NW; o <<= 1) {
@@ -559,7 +588,6 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 if (lane >= o) sc += n;
             }
             woff = __shfl_sync(kFull, sc, (warp + 31) & 31); // inclusive sum of the warps before this one
-            if (warp == 0) woff = 0.f;
         }
         const float p_in = woff + (incl - ls), p_out = woff + incl;
         // |chain - real prefix| <= k 2^-24 relative; the float scans above add < 64 further roundings
@@ -622,6 +650,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         // between the poll that sees E_w and the store of E_{w+1}.  Only mixed blocks are walked (16 real additions each,
         // every lane on its own registers, one shuffle per block).  seg = chain value after the last mixed block in
         // front of a lane (E_w if there is none); the replay below starts from it.
+        TL(6);
         int seg;
         {
             const int tag = *(volatile int *)&sh.cur_row + 1;
@@ -649,6 +678,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                 if (lane == 31) chain_publish(chain_s + 8u * (warp + 1), mixed ? carry : seg + ((seg & 1) ? g1 : g0), tag);
             }
         }
+        TL(7);
         float s_in; // exact chain value entering this thread's block = the CDF entry of the particle before it
         {   // every thread replays its own block from its exact entry state
             int badv = 0;
@@ -676,7 +706,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         }
         // the row's total = the chain value leaving the last warp (every warp's marks of P4 were zeroed in front of
         // barrier (4))
+        TL(8);
         float total = __int_as_float(chain_wait((unsigned)__cvta_generic_to_shared(sh.chain) + 8u * NW, *(volatile int *)&sh.cur_row + 1));
+        TL(9);
 
         // ---- P4: closed-form offspring boundaries (inference.py:251,260-264) and run marks ---------------------
         // particle j owns the positions [c_{j-1}, c_j); the boundary of the particle in front of this thread's block
@@ -758,7 +790,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             } else if (HAS_X && !FUSED) {
                 cp_async_wait_all();
             }
+            TL(10);
             __syncthreads(); // (8) run starts, staged latents and the scan's verdict visible
+            TL(11);
             if (kBulkX && attempt == 0 && tid == 0) sh.xphase ^= 1u; // (read again in front of the next row's barrier (8))
             if (attempt == 0 && sh.fail) {
                 // a binade bound was too optimistic (never observed): redo the row with the plain sequential chain
@@ -821,6 +855,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             if (lane == 31) sh.i2[warp] = inc;
             int excl = __shfl_up_sync(kFull, inc, 1);
             if (lane == 0) excl = 0;
+            TL(12);
             __syncthreads(); // (9) warp maxima of the run ids
             {
                 int sc = sh.i2[lane & (NW - 1)];
@@ -853,6 +888,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         // no barrier here: the next row touches the warp's own slice of bufW only after its barrier (1) ...
         // (bufX is restaged after barrier (1), bufM is rewritten after barrier (4)); the fused-model step writes the
         // staging row in its P1, hence:
+        TL(13);
         if (FUSED) __syncthreads();
     }
 }
@@ -944,3 +980,14 @@ int launch_smc_step_x_lg(const XStepParams &proto, int64_t B, int64_t K, cudaStr
 }
 
 } // namespace aesmc
+
+#if AESMC_X_TIMELINE
+extern "C" int aesmc_debug_timeline(long long *out_host, int reset) // profiling builds only (not declared in the public header)
+{
+    if (reset) {
+        static long long zeros[32 * 16];
+        return (int)cudaMemcpyToSymbol(aesmc::g_timeline, zeros, sizeof(zeros));
+    }
+    return (int)cudaMemcpyFromSymbol(out_host, aesmc::g_timeline, sizeof(long long) * 32 * 16);
+}
+#endif
