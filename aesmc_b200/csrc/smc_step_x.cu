@@ -235,7 +235,7 @@ template <int NW> struct Shared {
     float wmax[NW], part[NW], wsum[NW];
     int cnt[NW], i2[NW];
     float lse, total;
-    int bad, fail;
+    int bad, fail, slow;
     int2 chain[NW + 1];       // (bits of the exact chain value entering warp w's span, row tag); [NW]: the row's total
 };
 
@@ -266,12 +266,12 @@ template <int NW> __device__ __forceinline__ float across_max(const float *arr, 
 #endif
 #if AESMC_X_TIMELINE
 __device__ long long g_timeline[32 * 16]; // [warp][stage]: cycles since the row's start, summed over CTA 0's rows; [.][15] = rows
-#define TL(stage) do { if (blockIdx.x == 0 && lane == 0) g_timeline[16 * warp + (stage)] += clock64() - tl0; } while (0)
+#define TL(stage) do { if (blockIdx.x == 0 && lane == 0) atomicAdd((unsigned long long *)&g_timeline[16 * warp + (stage)], (unsigned long long)(clock64() - tl0)); } while (0) /* (a reduction without a return value: the warp does not wait for it) */
 #else
 #define TL(stage) do { } while (0)
 #endif
 #ifndef AESMC_X_FORCE_GENERAL
-#define AESMC_X_FORCE_GENERAL 0 // 1 (test builds): a quarter of the threads leave the call-free boundary loop at its fourth pair
+#define AESMC_X_FORCE_GENERAL 0 // 1 (test builds): every row raises sh.slow and has its marks redone by the general loop
 #endif
 #ifndef AESMC_X_FORCE_FAIL
 #define AESMC_X_FORCE_FAIL 0 // 1 (test builds): every row fails the scan's verification and takes the sequential redo path
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     __shared__ __align__(8) unsigned long long xbar; // completion of the latent row's bulk copy
     if (tid == 0) {
         sh.bad = 0;
+        sh.slow = 0;
         sh.xphase = 0;
         for (int i = 0; i <= NW; ++i) sh.chain[i] = make_int2(0, 0); // (tags are row + 1: never 0)
         if (kBulkX) mbar_init(&xbar, 1);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         const size_t off = (size_t)row * K; // P1 only: later phases use cur_off()
 #if AESMC_X_TIMELINE
         const long long tl0 = clock64();
-        if (blockIdx.x == 0 && lane == 0) g_timeline[16 * warp + 15] += 1;
+        if (blockIdx.x == 0 && lane == 0) atomicAdd((unsigned long long *)&g_timeline[16 * warp + 15], 1ull);
 #endif
         const float u32 = (float)p.u[row];
         if (tid == 0) { // (visible after barrier (1); the last readers are in front of the previous row's barrier (8))
@@ -713,6 +714,8 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         // ---- P4: closed-form offspring boundaries (inference.py:251,260-264) and run marks ---------------------
         // particle j owns the positions [c_{j-1}, c_j); the boundary of the particle in front of this thread's block
         // is recomputed from s_in (the same inputs, hence the same number, as its owner gets)
+        bool force_general = false, wl_filled = false;
+        volatile float wl[16]; // (volatile: the copy stays in the cold branch)
         for (int attempt = 0;; ++attempt) {
             float rcp = rcp_approx(total);
             rcp = __fmaf_rn(__fmaf_rn(-total, rcp, 1.0f), rcp, rcp);
@@ -727,19 +730,24 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
             const float tol32 = p.tol32;
             int idb = 16 * tid;
             asm volatile("" : "+r"(idb)); // (kept in a register: otherwise the thread index is re-read for every pair)
-            // THE HOT LOOP HAS NO CALLS: a call site inside it makes the 16 CDF entries live across a call, and all but
-            // the callee-saved few are then spilled for every thread of every row (measured: 4.6 % of the warp time
-            // waiting for those reloads).  Whatever needs an out-of-line routine -- the IEEE division outside the range
-            // the hoisted reciprocal is exact in, the reference's float64 comparison for a boundary within 2^-46 K of
-            // an integer -- leaves the loop for the rolled general loop below, which restarts at the pair it left.
-            int jd = 0, cp = 0;
-            if (__all_sync(kFull, safe)) { // one warp-uniform choice instead of a branch inside every pair
-                if (tid != 0) {
+            // THE HOT LOOP HAS NO CALLS AND NO EXITS.  A call site inside it makes the 16 CDF entries live across a call,
+            // and all but the callee-saved few are then spilled for every thread of every row (measured: 4.6 % of the
+            // warp time waiting for those reloads).  A goto out of it (tried first) moves the reconvergence point of
+            // every branch around it to its target: a lane in the 0.1 % fix-up branch then runs the rest of the loop
+            // apart from its warp (measured on warp 0, whose tid != 0 test wrapped such an exit: P4 took twice as long).
+            // So: a warp outside the range the hoisted reciprocal is the IEEE quotient in takes the rolled general loop
+            // as a whole (warp-uniform), and a boundary that needs the reference's float64 comparison (within 2^-46 K
+            // of an integer, ~1 in 10^7) only raises sh.slow: the row's marks are then redone by the general loop
+            // behind barrier (8).
+            int cp = 0;
+            if (!force_general && __all_sync(kFull, safe)) { // one warp-uniform choice instead of a branch inside every pair
+                {   // boundary of the particle in front of the block (0 for the row's first thread, whose s_in is 0)
                     const float q0 = __fmul_rn(s_in, rcp), n = __fmaf_rn(__fmaf_rn(-total, q0, s_in), rcp, q0);
                     const float tf = __fmaf_rn(n, Kf, -u32);
                     const float d = __fsub_rn(tf, __fsub_rn(__fadd_rn(tf, 12582912.0f), 12582912.0f));
                     cp = __float_as_int(__fadd_ru(tf, 12582912.0f)) - 0x4B400000;
-                    if (!(fabsf(d) > tol32) && !count_positions_near_x(n, u32, &sh.ulo, Kf, cp)) goto general;
+                    if (!(fabsf(d) > tol32) && !count_positions_near_x(n, u32, &sh.ulo, Kf, cp) && tid != 0) sh.slow = 1;
+                    if (tid == 0) cp = 0;
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
@@ -757,32 +765,35 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     unpack2(tmu, m0, m1);
                     int ca = __float_as_int(m0) - 0x4B400000;
                     int cb = __float_as_int(m1) - 0x4B400000;
-                    if (AESMC_X_FORCE_GENERAL && j == 6 && (tid & 3) == 1) { jd = j; goto general; }
+                    if (AESMC_X_FORCE_GENERAL && j == 6 && (tid & 63) == 1) sh.slow = 1;
                     if (!(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
                         float n0, n1;
                         unpack2(n2, n0, n1);
-                        if (!(fabsf(d0) > tol32) && !count_positions_near_x(n0, u32, &sh.ulo, Kf, ca)) { jd = j; goto general; }
-                        if (!(fabsf(d1) > tol32) && !count_positions_near_x(n1, u32, &sh.ulo, Kf, cb)) { jd = j; goto general; }
+                        if (!(fabsf(d0) > tol32) && !count_positions_near_x(n0, u32, &sh.ulo, Kf, ca)) sh.slow = 1;
+                        if (!(fabsf(d1) > tol32) && !count_positions_near_x(n1, u32, &sh.ulo, Kf, cb)) sh.slow = 1;
                     }
                     if (j == 14 && tid == NT - 1) cb = K; // last particle: positions up to 1.0 stay in range (Q5)
                     mark_run(marks_s, cp, ca, idb + j);
                     mark_run(marks_s, ca, cb, idb + j + 1);
                     cp = cb;
                 }
-                jd = 16;
-            }
-        general:
-            if (jd < 16) { // (a whole warp of a row with collapsed weights, else single lanes about once per 10^7 particles)
-                float wl[16];
+            } else { // (typically the first warp of a row with collapsed weights; every warp in the redo of a "slow" row)
+                // the CDF entries move to local memory in front of the calls and their registers are declared dead: live
+                // across a call they would be spilled where they are produced, in the hot path, for every thread
+                if (!wl_filled) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) wl[j] = w[j];
-                if (jd == 0) cp = tid ? count_positions_below_filtered_x(__fdiv_rn(s_in, total), &sh.u64, &sh.ulo, u32, K, Kf, tol32) : 0;
+                    for (int j = 0; j < 16; ++j) wl[j] = w[j];
+                    wl_filled = true;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = 0.f;
+                int c0 = tid ? count_positions_below_filtered_x(__fdiv_rn(s_in, total), &sh.u64, &sh.ulo, u32, K, Kf, tol32) : 0;
 #pragma unroll 1
-                for (int j = jd; j < 16; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     int c = count_positions_below_filtered_x(__fdiv_rn(wl[j], total), &sh.u64, &sh.ulo, u32, K, Kf, tol32);
                     if (j == 15 && tid == NT - 1) c = K;
-                    mark_run(marks_s, cp, c, idb + j);
-                    cp = c;
+                    mark_run(marks_s, c0, c, idb + j);
+                    c0 = c;
                 }
             }
             if (kBulkX) {
@@ -827,10 +838,20 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     const float4 v = redo[bl + i];
                     w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
                 }
+                wl_filled = false;
                 __syncthreads();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0);
                 __syncthreads();
+                continue;
+            }
+            if (!force_general && sh.slow) { // (CTA-uniform) some boundary needs the float64 comparison: one more trip
+                __syncthreads();               // through P4, every warp on the general loop
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bufM4[bl + i] = make_int4(0, 0, 0, 0);
+                if (tid == 0) sh.slow = 0;
+                __syncthreads();
+                force_general = true;
                 continue;
             }
             break;
