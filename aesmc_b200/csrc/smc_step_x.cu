@@ -186,7 +186,9 @@ __device__ __forceinline__ int count_positions_below_filtered_x(float cdf_entry,
 #endif
 // the warp chain of level 2: one 8-byte shared-memory word per warp, (value, tag), written and read as a unit
 #ifndef AESMC_X_CHAIN_SYNC
-#define AESMC_X_CHAIN_SYNC 1 // 0: volatile accesses, 1: st.release / ld.acquire at CTA scope, 2: shared-memory atomics
+#define AESMC_X_CHAIN_SYNC 1 // 0: volatile accesses, 1: st.relaxed / ld.relaxed at CTA scope (the record carries its own payload: no
+                             // other data is ordered by it, so no fence -- release semantics cost a MEMBAR.CTA per hand-off),
+                             // 2: shared-memory atomics (the racecheck control), 3: st.release / ld.acquire
 #endif
 __device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
 {
@@ -194,6 +196,8 @@ __device__ __forceinline__ void chain_publish(unsigned addr, int value, int tag)
 #if AESMC_X_CHAIN_SYNC == 0
     asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(addr), "l"(rec) : "memory");
 #elif AESMC_X_CHAIN_SYNC == 1
+    asm volatile("st.relaxed.cta.shared.b64 [%0], %1;" ::"r"(addr), "l"(rec) : "memory");
+#elif AESMC_X_CHAIN_SYNC == 3
     asm volatile("st.release.cta.shared.b64 [%0], %1;" ::"r"(addr), "l"(rec) : "memory");
 #else
     unsigned long long old;
@@ -207,6 +211,8 @@ __device__ __forceinline__ int chain_wait(unsigned addr, int tag)
 #if AESMC_X_CHAIN_SYNC == 0
         asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(rec) : "r"(addr) : "memory");
 #elif AESMC_X_CHAIN_SYNC == 1
+        asm volatile("ld.relaxed.cta.shared.b64 %0, [%1];" : "=l"(rec) : "r"(addr) : "memory");
+#elif AESMC_X_CHAIN_SYNC == 3
         asm volatile("ld.acquire.cta.shared.b64 %0, [%1];" : "=l"(rec) : "r"(addr) : "memory");
 #else
         asm volatile("atom.shared.or.b64 %0, [%1], 0;" : "=l"(rec) : "r"(addr) : "memory");

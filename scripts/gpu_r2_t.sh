@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over scripts/sanitize_step.py (round-2 kernels included).
 # racecheck runs twice: on the shipped build, where it reports the level-2 hand-off of smc_step_x.cu (chain_publish /
-# chain_wait: one 8-byte word per warp, st.release / ld.acquire, synchronisation BY a data race as racecheck sees it), and
+# chain_wait: one 8-byte word per warp, st.relaxed / ld.relaxed, synchronisation BY a data race as racecheck sees it), and
 # on build/variants/libaesmc_sync2.so (scripts/build_variants.sh sync2 "-DAESMC_X_CHAIN_SYNC=2": the same kernel with
 # that word written and polled by shared-memory atomics, 1.5x slower), which must be hazard-free.
 mkdir -p gpurun_out
