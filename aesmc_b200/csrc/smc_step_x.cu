@@ -431,7 +431,10 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         TL(0);
         __syncthreads(); // (1) warp maxima; every warp is done with the previous row's staged latents
         TL(1);
-        if (tid == 0) { sh.cur_row = row; sh.next_row = row + (int)gridDim.x; sh.fail = 0; }
+        if (tid == 0) {
+            sh.cur_row = row; sh.next_row = row + (int)gridDim.x; sh.fail = 0;
+            sh.chain[0] = make_int2(0, row + 1); // the chain value entering the row, 0.0f (level 2; read after barrier (4))
+        }
         if (HAS_X && !FUSED && !AESMC_X_ALIAS_X) { // stage this row's latents for the gather in P5
             const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(p.x_in + off) + gc;
 #pragma unroll
@@ -662,20 +665,22 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
         {
             const int tag = *(volatile int *)&sh.cur_row + 1;
             const unsigned chain_s = (unsigned)__cvta_generic_to_shared(sh.chain);
-            int E = 0;
+            // (every instruction between the poll that sees E_w and the store of E_{w+1} is on the row's critical path,
+            // ~10 cycles each on a busy SM: the map is applied as (E + c0) + (E & 1) (c1 - c0), two levels deep; warp 0
+            // polls like the others, its record (0, tag) was stored behind barrier (1); every lane stores the result)
             if (mixmask == 0u) {
-                const int G0 = __shfl_sync(kFull, g0, 31), G1 = __shfl_sync(kFull, g1, 31);
-                if (warp) E = chain_wait(chain_s + 8u * warp, tag);
-                const int ex = E + ((E & 1) ? G1 : G0);
-                if (lane == 0) chain_publish(chain_s + 8u * (warp + 1), ex, tag);
+                const int G0 = __shfl_sync(kFull, g0, 31), Gd = __shfl_sync(kFull, g1, 31) - G0;
+                const int E = chain_wait(chain_s + 8u * warp, tag);
+                chain_publish(chain_s + 8u * (warp + 1), (E + G0) + (E & 1) * Gd, tag);
                 seg = E;
             } else {
-                if (warp) E = chain_wait(chain_s + 8u * warp, tag);
+                const int pd = prev1 - prev0;
+                const int E = chain_wait(chain_s + 8u * warp, tag);
                 int carry = E, t = 0;
                 seg = E;
                 for (unsigned m = mixmask; m; m &= m - 1) {
                     const int pl = __ffs(m) - 1;
-                    float s = __int_as_float(carry + ((carry & 1) ? prev1 : prev0));
+                    float s = __int_as_float((carry + prev0) + (carry & 1) * pd);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) s = __fadd_rn(s, w[j]);
                     carry = __shfl_sync(kFull, __float_as_int(s), pl);
