@@ -14,19 +14,26 @@
 //     l + 32 i of that span: still 512 contiguous bytes per instruction), so both striped <-> blocked
 //     transposes stay inside the warp's own slice of the padded row buffer: __syncwarp instead of
 //     __syncthreads, twice per row;
-//   * warp boundaries are segment boundaries of the exact cumulative sum: the composition of the parity
-//     maps needs no cross-warp exchange (previously two barriers and an O(warps) dependent loop per
-//     thread); the walker visits ~5 more segments per row, each O(1);
+//   * warp boundaries are segment boundaries of the exact cumulative sum: inside a warp the parity maps of the
+//     non-mixed blocks compose by shuffles (level 1); across warps the exact chain value is handed from warp w to
+//     warp w + 1 through one tagged 8-byte shared-memory word (level 2: no walker warp, no barrier; a warp without
+//     mixed blocks forwards the value through the map of its 32 blocks, only mixed blocks -- ~10 per row -- are
+//     walked with real additions, on the registers of the lanes that own them);
 //   * cross-warp prefixes (row max, pairwise partials, approximate prefix, max-scan carry) are
 //     log-depth shuffles over one shared array instead of dependent loops over it;
 //   * the verification flag of the exact scan rides on the next barrier instead of its own;
-//   * 9 barriers per row instead of 15; no barrier at the end of a row (the latent row is staged
-//     after the next row's first barrier);
+//   * 7 barriers per row instead of 15 (warp 0 only arrives at the fourth: it heads level 2's serial chain); no
+//     barrier at the end of a row; the latent row is staged by one bulk asynchronous copy (cp.async.bulk +
+//     mbarrier) into the weight buffer once the weights are in registers, and the next row's inputs are pulled
+//     into L2 by cp.async.bulk.prefetch while this one is computed;
 //   * the maxima that scipy excludes from the sum are found by one compare per thread (its own maximum
 //     against the row's) instead of three instructions per particle; the IEEE-division range test and the
-//     clamp of the boundary count are hoisted out of the per-particle loop (the CDF is monotone: its first
-//     entry bounds the rest, and cdf / total <= 1 bounds the count by K); exp's denominator is evaluated
-//     negated instead of being negated afterwards.
+//     clamp of the boundary count are hoisted out of the per-particle loop (the CDF is monotone: the entry in
+//     front of a block bounds the rest, and cdf / total <= 1 bounds the count by K); exp's denominator is
+//     evaluated negated instead of being negated afterwards;
+//   * the per-row loop state (row index, mbarrier phase) lives in shared memory, and the per-particle loops
+//     contain neither calls nor exits: at 48 registers per thread (five CTAs per SM) anything live across a whole
+//     row or across a call site is spilled, and a spill reload in this kernel is an L2 round trip.
 //
 // Everything it cannot take (other K, vector latents, fast mode, the fused-model step, no resampling)
 // stays with smc_step_reg.cu / smc_step.cu / smc_step_large.cu.
