@@ -49,6 +49,7 @@ _PROTOTYPES = {
     "aesmc_normal_log_prob_bwd_f32": [_vp, _int, _vp, _int, ctypes.c_float, _vp, ctypes.c_float, _vp, _i64, _i64, _vp, _vp,
                                       _vp, _vp],
     "aesmc_selftest_expf": [_vp, _vp],
+    "aesmc_debug_force_rare_paths": [_int],
     "aesmc_log_ess_f32": [_vp, _i64, _i64, _vp, _vp],
     "aesmc_log_ess_f64": [_vp, _i64, _i64, _vp, _vp],
     "aesmc_weighted_moments_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp],

@@ -58,6 +58,7 @@ int launch_iota_index(int64_t, int64_t, int32_t *, cudaStream_t);
 int launch_index_widen(const int32_t *, int64_t *, int64_t, cudaStream_t);
 int launch_index_narrow(const int64_t *, int32_t *, int64_t, cudaStream_t);
 int launch_selftest_expf(unsigned long long *, cudaStream_t);
+void smc_step_x_set_debug_force(int bits);
 int normal_log_prob_f32(const float *, int, const float *, int, float, const float *, float, float, float, int64_t, int64_t,
                         float *, cudaStream_t);
 int normal_log_prob_bwd_f32(const float *, int, const float *, int, float, const float *, float, const float *, int64_t,
@@ -339,6 +340,15 @@ int aesmc_selftest_expf(uint64_t *out2, void *stream)
     const char *fn = "aesmc_selftest_expf";
     REQUIRE(out2 != nullptr, fn);
     return launch_selftest_expf(reinterpret_cast<unsigned long long *>(out2), S(stream));
+}
+
+int aesmc_debug_force_rare_paths(int bits)
+{
+    static int current = 0;
+    const int prev = current;
+    current = bits;
+    smc_step_x_set_debug_force(bits);
+    return prev;
 }
 
 int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream)

@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { s = __fadd_rn(s, w[j]); w[j] = s; }
             }
-            if (AESMC_X_FORCE_FAIL) badv = 1;
+            if (AESMC_X_FORCE_FAIL || (p.debug_force & 1)) badv = 1;
             if (badv && !(AESMC_X_ABLATE & 16)) sh.fail = 1; // read after barrier (8)
         }
         // the row's total = the chain value leaving the last warp (every warp's marks of P4 were zeroed in front of
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
                     unpack2(tmu, m0, m1);
                     int ca = __float_as_int(m0) - 0x4B400000;
                     int cb = __float_as_int(m1) - 0x4B400000;
-                    if (AESMC_X_FORCE_GENERAL && j == 6 && (tid & 63) == 1) sh.slow = 1;
+                    if ((AESMC_X_FORCE_GENERAL || (p.debug_force & 2)) && j == 6 && (tid & 63) == 1) sh.slow = 1;
                     if (!(fminf(fabsf(d0), fabsf(d1)) > tol32)) { // ~0.1 %: the exact comparison
                         float n0, n1;
                         unpack2(n2, n0, n1);
@@ -948,6 +948,9 @@ __global__ void __launch_bounds__(NT, (XConfig<HAS_X, FUSED>::kThreadsPerSM / NT
     }
 }
 
+static int g_debug_force = 0;
+void smc_step_x_set_debug_force(int bits) { g_debug_force = bits; }
+
 static int x_sm_count()
 {
     static int n = 0;
@@ -1017,6 +1020,7 @@ int launch_smc_step_x(const float *a, const float *b, const float *c, const doub
     p.a = a; p.b = b; p.c = c; p.u = u; p.B = (int)B; p.log_w = log_w; p.lse = lse; p.idx = idx;
     p.x_in = x_in; p.x_out = x_out; p.flags = flags;
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f; // K*2^-23 + 2^-24
+    p.debug_force = g_debug_force;
     return x_in != nullptr ? dispatch_x<true, false>(p, B, K, stream) : dispatch_x<false, false>(p, B, K, stream);
 }
 
@@ -1031,6 +1035,7 @@ int launch_smc_step_x_lg(const XStepParams &proto, int64_t B, int64_t K, cudaStr
     XStepParams p = proto;
     p.B = (int)B;
     p.tol32 = (float)K * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
+    p.debug_force = g_debug_force;
     return dispatch_x<true, true>(p, B, K, stream);
 }
 

@@ -15,6 +15,8 @@ struct XStepParams {
     float *x_out;
     int32_t *flags;
     float tol32;
+    int debug_force;      // test hook (aesmc_debug_force_rare_paths): bit 0 every row fails the scan's verification (sequential redo),
+                          // bit 1 every row raises the float64-comparison flag (marks redone by the general loop)
     // ---- fused scalar linear-Gaussian model (FUSED instances, aesmc_smc_step_lg_f32): the user model's sampling
     // and its three log-densities are evaluated in P1 instead of being read from HBM
     const float *x_prev;  // [B,K] resampled latents of the previous step, NULL at t = 0
@@ -30,6 +32,7 @@ struct XStepParams {
     const unsigned long long *seed_dev; // non-NULL: the Philox key is read from device memory (CUDA-graph replays)
 };
 
+void smc_step_x_set_debug_force(int bits);
 bool smc_step_x_supported(int64_t K, int mode, const void *idx, const void *x_in, int64_t D);
 int launch_smc_step_x(const float *a, const float *b, const float *c, const double *u, int64_t B, int64_t K,
                       float *log_w, float *lse, int32_t *idx, const float *x_in, float *x_out, int32_t *flags,

@@ -217,6 +217,12 @@ int aesmc_normal_log_prob_bwd_f32(const float *value, int value_kind, const floa
  * -inf.  out2: device uint64[2] = {number of mismatching inputs, bit pattern of one of them}. */
 int aesmc_selftest_expf(uint64_t *out2, void *stream);
 
+/* Test hook: force the exact row kernel's rare paths on every row of the following launches (0 = off, the default).
+ * bit 0: the exact scan's verification fails (the row is redone with the plain sequential chain); bit 1: a boundary is
+ * reported as needing the reference's float64 comparison (the row's run marks are redone by the general loop).  Results
+ * must not change (tests/test_step_parity_gpu.py).  Process-wide, not thread-safe; returns the previous value. */
+int aesmc_debug_force_rare_paths(int bits);
+
 /* statistics.log_ess (statistics.py:79-91): 2*lse(lw) - lse(2*lw) per row. */
 int aesmc_log_ess_f32(const float *log_w, int64_t B, int64_t K, float *out, void *stream);
 int aesmc_log_ess_f64(const double *log_w, int64_t B, int64_t K, double *out, void *stream);

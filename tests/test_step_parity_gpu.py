@@ -397,3 +397,41 @@ def test_second_generation_row_kernel_vs_oracle(cuda, K, B, with_x):
     assert fl1 == 0
     assert np.array_equal(idx1.cpu().numpy(), np.minimum(idx_ref[:64], K - 1).astype(np.int32))
     assert np.array_equal(bits(lse1.cpu().numpy()), bits(lse_ref[:64]))
+
+
+@pytest.mark.parametrize("bits_forced", [1, 2, 3])
+@pytest.mark.parametrize("K,B", [(1024, 900), (4096, 300), (16384, 40)])
+def test_second_generation_row_kernel_rare_paths_forced(cuda, K, B, bits_forced):
+    """The two paths of smc_step_x.cu that real data (almost) never takes, forced on every row through the test hook
+    aesmc_debug_force_rare_paths: bit 0 = the exact scan's verification fails and the row is redone with the plain
+    sequential chain, bit 1 = a boundary asks for the reference's float64 comparison and the row's run marks are
+    redone by the general loop.  Plain and fused-gather call shapes, flat to collapsed weights: same bits as the oracle."""
+    rng = np.random.default_rng(7 * K + bits_forced)
+    spread = rng.uniform(0.2, 12.0, (B, 1))
+    a = (rng.standard_normal((B, K)) * spread - 1.4).astype(np.float32)
+    b = (rng.standard_normal((B, K)) * 0.5).astype(np.float32)
+    c = (rng.standard_normal((B, K)) * 0.5).astype(np.float32)
+    a[5, ::3] = -np.inf
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    u = rng.random(B)
+    u[1] = 0.0
+    u[2] = np.nextafter(1.0, 0.0)
+    lw_ref = oracle.log_weight(a, b, c)
+    idx_ref, st, lse_ref, _, _ = oracle.sample_ancestral_index(lw_ref, u, return_parts=True)
+    assert st == 0
+    lib = _lib.load()
+    prev = lib.aesmc_debug_force_rare_paths(bits_forced)
+    try:
+        (log_w, lse, idx, xr), fl = run_step(a, u, cuda, b=b, c=c, x=x)
+        (_, lse1, idx1, _), fl1 = run_step(lw_ref[:64], u[:64], cuda)
+    finally:
+        lib.aesmc_debug_force_rare_paths(prev)
+    assert fl == 0 and fl1 == 0
+    got = idx.cpu().numpy()
+    assert np.array_equal(bits(log_w.cpu().numpy()), bits(lw_ref))
+    assert np.array_equal(bits(lse.cpu().numpy()), bits(lse_ref))
+    wrong = np.nonzero((got != np.minimum(idx_ref, K - 1)).any(axis=1))[0]
+    assert wrong.size == 0, "rows with index mismatches: %s" % wrong[:10]
+    assert np.array_equal(xr.cpu().numpy(), np.take_along_axis(x, got.astype(np.int64), axis=1))
+    assert np.array_equal(idx1.cpu().numpy(), np.minimum(idx_ref[:64], K - 1).astype(np.int32))
+    assert np.array_equal(bits(lse1.cpu().numpy()), bits(lse_ref[:64]))
