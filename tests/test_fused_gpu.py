@@ -309,3 +309,33 @@ def test_fused_scalar_matches_cpu_port_on_shared_noise(cuda, proposal):
     assert same_rows.sum() >= B - 2
     dz = np.abs(got["log_marginal_likelihood"].cpu().numpy() - ref["log_marginal_likelihood"].numpy())
     assert dz[same_rows].max() < 1e-3 and dz.max() < 1.0
+
+
+@pytest.mark.parametrize("proposal", ["bootstrap", AFFINE])
+def test_fused_step_rare_paths_forced(cuda, proposal):
+    """The fused-model instance of the exact row kernel with its two rare paths forced on every row (test hook
+    aesmc_debug_force_rare_paths: sequential redo after a failed verification, float64 redo of the run marks): the
+    filter's outputs keep their bits."""
+    from aesmc_b200 import _lib
+    T, B, K = 6, 9, 4096
+    model = fused.ScalarLinearGaussianSSM(0.2, 1.1, 0.9, 0.05, 0.7, 1.3, -0.1, 0.5, proposal=proposal, device=cuda)
+    obs = torch.from_numpy(lgssm.simulate(T, B, seed=3)).to(cuda)
+    noise = torch.randn(T, B, K, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    u = np.random.default_rng(1).random((T - 1, B))
+    kw = dict(return_log_marginal_likelihood=True, return_latents=True, return_log_weights=True, return_ancestral_indices=True)
+    with torch.no_grad():
+        ref = fused.infer_fused(model, obs, K, uniforms=u, noise=noise, **kw)
+    lib = _lib.load()
+    for forced in (1, 2, 3):
+        prev = lib.aesmc_debug_force_rare_paths(forced)
+        try:
+            with torch.no_grad():
+                got = fused.infer_fused(model, obs, K, uniforms=u, noise=noise, **kw)
+            torch.cuda.synchronize()
+        finally:
+            lib.aesmc_debug_force_rare_paths(prev)
+        assert torch.equal(got["log_marginal_likelihood"], ref["log_marginal_likelihood"]), forced
+        for a, b in zip(got["ancestral_indices"], ref["ancestral_indices"]):
+            assert torch.equal(a, b), forced
+        for t in range(T):
+            assert torch.equal(got["latents"][t], ref["latents"][t]) and torch.equal(got["log_weights"][t], ref["log_weights"][t])
