@@ -201,7 +201,11 @@ def run_native(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("smc_step_kernel_%s" % mode)
-    roofline = {"bound": "hbm", "kernel": "smc_step_kernel<%s>" % mode, "achieved": round(achieved, 1), "peak": peak,
+    # (what aesmc_smc_step_f32 dispatches to at this shape: smc_step_x.cu's row kernel in exact mode for K = 1024 ... 16384
+    # and a scalar latent, smc_step_reg.cu's otherwise)
+    xk = mode == "exact" and D == 1 and K in (1024, 2048, 4096, 8192, 16384)
+    kname = "smc_step_x_kernel<%d,1,0> (exact)" % (K // 16) if xk else "smc_step_reg_kernel (%s)" % mode
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "bytes_per_launch": bytes_per_launch, "launch_ms": round(kernel_ms, 4), "peak_source": peak_src}
 
